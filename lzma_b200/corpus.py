@@ -153,9 +153,10 @@ def alone_from_lzma2_chunk(data: bytes, lc=3, lp=0, pb=2, dict_size=1 << 16, pre
 # ---------- parallel builders for bench.py ----------
 
 def _job_text_alone(args):
+    import zlib
     seed, size, kw = args
     d = text_block(seed, size)
-    return compress_alone(d, **kw)
+    return compress_alone(d, **kw), zlib.crc32(d)
 
 
 def _job_text_lzma2(args):
@@ -163,14 +164,18 @@ def _job_text_lzma2(args):
     return compress_raw_lzma2(text_block(seed, size), **kw)
 
 
-def build_alone_streams(n: int, size: int, seed0: int = 0, workers: int | None = None, **kw):
-    """n independent .lzma streams of `size` text-like bytes (stream i uses seed seed0+i)."""
+def build_alone_streams(n: int, size: int, seed0: int = 0, workers: int | None = None, with_crc: bool = False, **kw):
+    """n independent .lzma streams of `size` text-like bytes (stream i uses seed seed0+i).
+    with_crc: also return the CRC32 of each plaintext."""
     workers = workers or os.cpu_count() or 1
     jobs = [(seed0 + i, size, kw) for i in range(n)]
     if workers == 1 or n < 4:
-        return [_job_text_alone(j) for j in jobs]
-    with ProcessPoolExecutor(max_workers=min(workers, n)) as ex:
-        return list(ex.map(_job_text_alone, jobs, chunksize=max(1, n // (workers * 8))))
+        out = [_job_text_alone(j) for j in jobs]
+    else:
+        with ProcessPoolExecutor(max_workers=min(workers, n)) as ex:
+            out = list(ex.map(_job_text_alone, jobs, chunksize=max(1, n // (workers * 8))))
+    streams, crcs = [o[0] for o in out], [o[1] for o in out]
+    return (streams, crcs) if with_crc else streams
 
 
 def build_lzma2_stream(n_blocks: int, block: int, seed0: int = 0, workers: int | None = None, **kw) -> bytes:

@@ -1,0 +1,676 @@
+// lzgpu.cu -- sm_100a decode kernel + the host side of the C ABI in include/lzgpu.h.
+//
+// Host side = what the reference's readers do around the hot loop, re-stated for a
+// batch: header parsing (reader1.go:77-147,178-221), LZMA2 chunk framing
+// (reader2.go:100-214), plus what the reference never needed: unit discovery, a
+// size-balanced scheduler over GPUs, and the H2D / D2H plumbing.
+// There is no CPU decode path in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "lzgpu_prep.h"
+#include "lzgpu_unit.cuh"
+
+using namespace lzgpu;
+
+// ------------------------------------------------------------------ kernel
+struct KArgs {
+    const lzgpu_unit *units;     // device copy of the plan's units (ALONE already rebased to RAW)
+    const int32_t *order;        // launch slot -> unit index (longest compressed first)
+    const uint8_t *in_base;
+    uint8_t *out_base;
+    lzgpu_result *results;
+    uint16_t *lit_ws;            // literal tables in HBM for units with lc+lp > 4
+    uint64_t lit_ws_stride;      // uint16 elements per slot
+    uint32_t lit_bits_cap;       // literal-table capacity of this launch, as lc+lp
+    uint32_t slot0;              // first slot of this launch in `order`
+};
+
+// One warp per CTA, one unit per warp.  Fixed tables (3.7 KB) always in shared
+// memory; literal tables in shared memory when lc+lp <= 4 (<= 24 KB), else in HBM.
+template <bool kLitGlobal>
+__global__ void __launch_bounds__(32) lzgpu_decode_kernel(const KArgs a) {
+    extern __shared__ __align__(16) uint16_t smem_probs[];
+    const uint32_t slot = a.slot0 + blockIdx.x;
+    const int32_t ui = a.order[slot];
+    const lzgpu_unit u = a.units[ui];
+    uint16_t *P = smem_probs;
+    uint16_t *L = kLitGlobal ? a.lit_ws + (size_t)blockIdx.x * a.lit_ws_stride : smem_probs + P_LIT;
+    UnitIO io;
+    io.in = a.in_base + u.in_off;
+    io.in_len = u.in_len;
+    io.out = a.out_base + u.out_off;
+    io.out_cap = u.out_cap;
+    lzgpu_result &res = a.results[ui];
+    if (u.kind == LZGPU_KIND_LZMA2_GROUP) run_unit_lzma2(u, io, P, L, a.lit_bits_cap, res);
+    else run_unit_lzma1(u, io, P, L, res);
+}
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e_ = (expr);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail(LZGPU_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));   \
+    } while (0)
+
+extern "C" int lzgpu_abi_version(void) { return LZGPU_ABI_VERSION; }
+
+extern "C" int lzgpu_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        g_last_error = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" const char *lzgpu_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" const char *lzgpu_status_name(int s) {
+    switch (s) {
+        case LZGPU_OK: return "OK";
+        case LZGPU_OK_INPUT_EXHAUSTED: return "OK_INPUT_EXHAUSTED";
+        case LZGPU_RESULT_ERROR: return "RESULT_ERROR";
+        case LZGPU_INCORRECT_PROPERTIES: return "INCORRECT_PROPERTIES";
+        case LZGPU_UNEXPECTED_EOF: return "UNEXPECTED_EOF";
+        case LZGPU_OUTPUT_OVERFLOW: return "OUTPUT_OVERFLOW";
+        case LZGPU_DICT_OUT_OF_RANGE: return "DICT_OUT_OF_RANGE";
+        case LZGPU_UNEXPECTED_LZMA2_CODE: return "UNEXPECTED_LZMA2_CODE";
+        case LZGPU_NOT_RUN: return "NOT_RUN";
+    }
+    return "?";
+}
+
+// ------------------------------------------------------------------ header helpers
+extern "C" int lzgpu_decode_prop(uint8_t d, uint8_t *lc, uint8_t *pb, uint8_t *lp) {
+    if (d >= 9 * 5 * 5) return LZGPU_INCORRECT_PROPERTIES;   // reader1.go:211-213
+    *lc = d % 9;
+    d /= 9;
+    *pb = d / 5;
+    *lp = d % 5;
+    return LZGPU_OK;
+}
+extern "C" uint32_t lzgpu_decode_dict_size(const uint8_t p[4]) {
+    uint32_t d = (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24;
+    return d < 4096u ? 4096u : d;                            // lzmaDicMin, reader1.go:199-201
+}
+extern "C" uint64_t lzgpu_decode_unpack_size(const uint8_t h[8]) {
+    uint64_t n = 0;
+    for (int i = 0; i < 8; i++) n |= (uint64_t)h[i] << (8 * i);
+    return n;
+}
+extern "C" uint32_t lzgpu_decode_dict_size2(uint8_t b) { return (uint32_t)(2 | (b & 1)) << (b / 2 + 11); }
+
+extern "C" int lzgpu_parse_alone_header(const uint8_t *in, uint64_t in_len, lzgpu_unit *u) {
+    if (in_len < 1) return LZGPU_UNEXPECTED_EOF;             // bare io.EOF, reader1.go:78-81
+    uint8_t lc, pb, lp;
+    if (lzgpu_decode_prop(in[0], &lc, &pb, &lp) != LZGPU_OK) return LZGPU_INCORRECT_PROPERTIES;
+    if (in_len < 13) return LZGPU_UNEXPECTED_EOF;            // "decode dict size/unpack size: EOF"
+    u->kind = LZGPU_KIND_LZMA1_ALONE;
+    u->lc = lc; u->lp = lp; u->pb = pb;
+    u->lit_bits = (uint8_t)(lc + lp);
+    u->dict_size = lzgpu_decode_dict_size(in + 1);
+    u->unpack_size = lzgpu_decode_unpack_size(in + 5);
+    return LZGPU_OK;
+}
+
+// ------------------------------------------------------------------ LZMA2 scanner
+extern "C" int64_t lzgpu_scan_lzma2(const uint8_t *in, uint64_t in_len, uint32_t dict_size,
+                                    lzgpu_unit *units, int64_t max_units,
+                                    uint64_t *total_out, int32_t *stream_status) {
+    if (dict_size < 4096u) dict_size = 8u << 20;             // validateDictSize, reader2.go:88-91
+    uint64_t pos = 0, out = 0;
+    uint32_t props = 0;          // r.header[5], initially 0 (Q8)
+    bool seen_lzma = false;      // r.lzmaReader != nil
+    int64_t n = 0;
+    int32_t sst = LZGPU_OK;
+
+    lzgpu_unit cur;
+    auto open_unit = [&](uint64_t at) {
+        memset(&cur, 0, sizeof cur);
+        cur.kind = LZGPU_KIND_LZMA2_GROUP;
+        cur.in_off = at;
+        cur.out_off = out;
+        cur.dict_size = dict_size;
+        const uint32_t p = props < 225 ? props : 0;
+        cur.lc = (uint8_t)(p % 9);
+        cur.lp = (uint8_t)((p / 9) % 5);
+        cur.pb = (uint8_t)((p / 9) / 5);
+        cur.lit_bits = 0;
+        cur.flags = seen_lzma ? 0u : LZGPU_UF_LZMA2_FRESH;
+    };
+    auto close_unit = [&](uint64_t end, bool last) {
+        cur.in_len = end - cur.in_off;
+        cur.out_cap = out - cur.out_off;
+        cur.unpack_size = cur.out_cap;
+        if (last) cur.flags |= LZGPU_UF_LZMA2_LAST;
+        if (n < max_units && units) units[n] = cur;
+        n++;
+    };
+    open_unit(0);
+
+    for (;;) {
+        if (pos >= in_len) { sst = LZGPU_UNEXPECTED_EOF; break; }          // reader2.go:103-110
+        const uint32_t c = in[pos];
+        if (c == 0 || (c >= 3 && c < 0x80)) { pos += 1; break; }           // end of stream (and Q6)
+        const uint32_t hl = c < 0x80 ? 3 : (c < 0xC0 ? 5 : 6);
+        if (in_len - pos < hl) { pos = in_len; sst = LZGPU_UNEXPECTED_EOF; break; }
+        uint32_t usz = ((uint32_t)in[pos + 1] << 8 | in[pos + 2]);
+        uint32_t pl;
+        if (c >= 0x80) {
+            usz |= (c & 0x1Fu) << 16;
+            pl = (((uint32_t)in[pos + 3] << 8) | in[pos + 4]) + 1;
+        }
+        usz += 1;
+        if (c < 0x80) pl = usz;
+
+        // A unit may begin at a dictionary reset provided the first LZMA chunk from here
+        // on resets the coder state too (0xE0.. does; after 0x01 look ahead).
+        if ((c == 1 || c >= 0xE0) && pos != cur.in_off) {
+            bool cut = true;
+            if (c == 1) {
+                uint64_t q = pos;
+                for (;;) {
+                    if (q >= in_len) break;
+                    const uint32_t cc = in[q];
+                    if (cc == 0 || (cc >= 3 && cc < 0x80)) break;
+                    if (cc >= 0x80) { cut = cc >= 0xA0; break; }
+                    if (q != pos && cc == 1) break;
+                    if (in_len - q < 3) break;
+                    q += 3 + (((uint64_t)in[q + 1] << 8 | in[q + 2]) + 1);
+                }
+            }
+            if (cut) {
+                close_unit(pos, false);
+                open_unit(pos);
+            }
+        }
+        if (c >= 0xC0) props = in[pos + 5];
+        if (c >= 0x80) {
+            if (props < 225) {
+                const uint32_t lb = props % 9 + (props / 9) % 5;
+                if (lb > cur.lit_bits) cur.lit_bits = (uint8_t)lb;
+            }
+            seen_lzma = true;
+        }
+        out += usz;
+        if (in_len - pos - hl < pl) { pos = in_len; sst = LZGPU_UNEXPECTED_EOF; break; }
+        pos += hl + pl;
+    }
+    // the last unit owns everything up to the end of the buffer, so that the device walk
+    // sees exactly what the reference would read
+    close_unit(in_len, true);
+    if (total_out) *total_out = out;
+    if (stream_status) *stream_status = sst;
+    return n;
+}
+
+// ------------------------------------------------------------------ scheduler
+extern "C" int lzgpu_shard_units(const lzgpu_unit *units, int64_t n, int n_shards, int32_t *shard_of_unit) {
+    if (n_shards < 1 || n < 0 || (n > 0 && (!units || !shard_of_unit))) return fail(LZGPU_E_INVALID, "shard_units: bad arguments");
+    std::vector<int64_t> idx((size_t)n);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return units[a].in_len > units[b].in_len; });
+    std::vector<uint64_t> load((size_t)n_shards, 0);
+    for (int64_t k = 0; k < n; k++) {
+        int best = 0;
+        for (int s = 1; s < n_shards; s++) if (load[s] < load[best]) best = s;
+        shard_of_unit[idx[k]] = best;
+        load[best] += units[idx[k]].in_len + 64;   // +64: every unit costs a table reset even when tiny
+    }
+    return LZGPU_E_OK;
+}
+
+// ------------------------------------------------------------------ context / plan
+struct DevState {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    // grow-only staging for the host-buffer entry point
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    uint64_t in_cap = 0, out_cap = 0;
+};
+
+struct lzgpu_ctx {
+    std::vector<DevState> devs;
+    std::mutex mu;
+};
+
+struct Launch {
+    uint32_t lit_bits;   // class
+    bool lit_global;
+    uint32_t slot0, count;
+    size_t smem;
+};
+
+struct lzgpu_plan {
+    lzgpu_ctx *ctx = nullptr;
+    int dev_index = 0;
+    int64_t n = 0;
+    uint64_t in_size = 0, out_size = 0;
+    std::vector<lzgpu_unit> units;        // device view (ALONE rebased)
+    std::vector<lzgpu_result> preset;     // results decided on the host (status != NOT_RUN)
+    std::vector<uint8_t> was_alone;       // unit arrived as LZMA1_ALONE (13-byte header rebased away)
+    std::vector<int32_t> order;
+    std::vector<Launch> launches;
+    lzgpu_unit *d_units = nullptr;
+    int32_t *d_order = nullptr;
+    lzgpu_result *d_results = nullptr;
+    uint16_t *d_lit_ws = nullptr;
+    uint64_t lit_ws_stride = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool launched = false;
+};
+
+extern "C" int lzgpu_ctx_create(const int *devices, int n_devices, lzgpu_ctx **out) {
+    if (!out) return fail(LZGPU_E_INVALID, "ctx_create: null out");
+    const int avail = lzgpu_device_count();
+    if (avail <= 0) return fail(LZGPU_E_NO_DEVICE, "no CUDA device visible: this library has no CPU decode path (" + g_last_error + ")");
+    std::vector<int> ids;
+    if (n_devices <= 0 || !devices) for (int i = 0; i < avail; i++) ids.push_back(i);
+    else for (int i = 0; i < n_devices; i++) ids.push_back(devices[i]);
+    lzgpu_ctx *c = new lzgpu_ctx();
+    for (int id : ids) {
+        if (id < 0 || id >= avail) { lzgpu_ctx_destroy(c); return fail(LZGPU_E_INVALID, "ctx_create: device ordinal out of range"); }
+        DevState d;
+        d.device = id;
+        cudaError_t e = cudaSetDevice(id);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { lzgpu_ctx_destroy(c); return fail(LZGPU_E_CUDA, std::string("ctx_create: ") + cudaGetErrorString(e)); }
+        c->devs.push_back(d);
+    }
+    *out = c;
+    return LZGPU_E_OK;
+}
+
+extern "C" void lzgpu_ctx_destroy(lzgpu_ctx *c) {
+    if (!c) return;
+    for (auto &d : c->devs) {
+        cudaSetDevice(d.device);
+        if (d.stream) cudaStreamDestroy(d.stream);
+        if (d.d_in) cudaFree(d.d_in);
+        if (d.d_out) cudaFree(d.d_out);
+    }
+    delete c;
+}
+
+extern "C" int lzgpu_ctx_device_count(const lzgpu_ctx *c) { return c ? (int)c->devs.size() : 0; }
+
+extern "C" void lzgpu_plan_destroy(lzgpu_plan *p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->devs[p->dev_index].device);
+    if (p->d_units) cudaFree(p->d_units);
+    if (p->d_order) cudaFree(p->d_order);
+    if (p->d_results) cudaFree(p->d_results);
+    if (p->d_lit_ws) cudaFree(p->d_lit_ws);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    delete p;
+}
+
+static size_t smem_bytes(uint32_t lit_bits, bool lit_global) {
+    return sizeof(uint16_t) * ((size_t)P_FIXED + (lit_global ? 0 : ((size_t)0x300 << lit_bits)));
+}
+
+extern "C" int lzgpu_plan_create(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *units, int64_t n,
+                                 uint64_t in_size, uint64_t out_size, lzgpu_plan **out) {
+    if (!ctx || !out || n < 0 || (n > 0 && !units)) return fail(LZGPU_E_INVALID, "plan_create: bad arguments");
+    if (dev_index < 0 || dev_index >= (int)ctx->devs.size()) return fail(LZGPU_E_INVALID, "plan_create: dev_index out of range");
+    if (n > INT32_MAX) return fail(LZGPU_E_INVALID, "plan_create: too many units");
+    CUDA_TRY(cudaSetDevice(ctx->devs[dev_index].device));
+    lzgpu_plan *p = new lzgpu_plan();
+    p->ctx = ctx;
+    p->dev_index = dev_index;
+    p->n = n;
+    p->in_size = in_size;
+    p->out_size = out_size;
+    p->units.assign(units, units + n);
+    p->preset.resize((size_t)n);
+    p->was_alone.assign((size_t)n, 0);
+    std::vector<int32_t> runnable;
+    for (int64_t i = 0; i < n; i++) {
+        lzgpu_unit &u = p->units[(size_t)i];
+        lzgpu_result &r = p->preset[(size_t)i];
+        if (u.in_off > in_size || u.in_len > in_size - u.in_off || u.out_off > out_size || u.out_cap > out_size - u.out_off) {
+            lzgpu_plan_destroy(p);
+            return fail(LZGPU_E_INVALID, "plan_create: unit " + std::to_string(i) + " lies outside the buffers");
+        }
+        if (u.kind != LZGPU_KIND_LZMA1_ALONE && u.kind != LZGPU_KIND_LZMA1_RAW && u.kind != LZGPU_KIND_LZMA2_GROUP) {
+            lzgpu_plan_destroy(p);
+            return fail(LZGPU_E_INVALID, "plan_create: unknown unit kind");
+        }
+        bool alone = false;
+        const bool run = prepare_unit(u, r, &alone);
+        r.device = ctx->devs[dev_index].device;
+        p->was_alone[(size_t)i] = alone;
+        if (!run) continue;
+        runnable.push_back((int32_t)i);
+    }
+    // launch order: by literal-table class, then longest compressed input first (LPT within the GPU)
+    std::stable_sort(runnable.begin(), runnable.end(), [&](int32_t a, int32_t b) {
+        const lzgpu_unit &x = p->units[(size_t)a], &y = p->units[(size_t)b];
+        const uint32_t cx = x.lit_bits <= 4 ? x.lit_bits : 100, cy = y.lit_bits <= 4 ? y.lit_bits : 100;
+        if (cx != cy) return cx < cy;
+        return x.in_len > y.in_len;
+    });
+    p->order = runnable;
+    uint32_t s = 0;
+    uint64_t ws_slots = 0;
+    uint32_t ws_bits = 0;
+    while (s < runnable.size()) {
+        const lzgpu_unit &u0 = p->units[(size_t)runnable[s]];
+        const bool g = u0.lit_bits > 4;
+        uint32_t e = s;
+        uint32_t maxbits = 0;
+        while (e < runnable.size()) {
+            const lzgpu_unit &ue = p->units[(size_t)runnable[e]];
+            if (g ? ue.lit_bits <= 4 : ue.lit_bits != u0.lit_bits) break;
+            maxbits = std::max<uint32_t>(maxbits, ue.lit_bits);
+            e++;
+        }
+        if (g) {
+            // HBM literal tables: bound the workspace by launching in waves
+            const uint64_t per = (uint64_t)0x300 << maxbits;
+            const uint64_t max_slots = std::max<uint64_t>(1, ((uint64_t)2 << 30) / (per * 2));
+            ws_bits = std::max(ws_bits, maxbits);
+            for (uint32_t w = s; w < e; w += (uint32_t)max_slots) {
+                const uint32_t cnt = (uint32_t)std::min<uint64_t>(max_slots, e - w);
+                p->launches.push_back({maxbits, true, w, cnt, smem_bytes(maxbits, true)});
+                ws_slots = std::max<uint64_t>(ws_slots, cnt);
+            }
+        } else {
+            p->launches.push_back({maxbits, false, s, e - s, smem_bytes(maxbits, false)});
+        }
+        s = e;
+    }
+    auto bail = [&](cudaError_t e, const char *what) {
+        std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+        lzgpu_plan_destroy(p);
+        return fail(e == cudaErrorMemoryAllocation ? LZGPU_E_NOMEM : LZGPU_E_CUDA, m);
+    };
+    cudaError_t e;
+    if (n > 0) {
+        if ((e = cudaMalloc(&p->d_units, sizeof(lzgpu_unit) * (size_t)n)) != cudaSuccess) return bail(e, "cudaMalloc units");
+        if ((e = cudaMalloc(&p->d_results, sizeof(lzgpu_result) * (size_t)n)) != cudaSuccess) return bail(e, "cudaMalloc results");
+        if ((e = cudaMalloc(&p->d_order, sizeof(int32_t) * std::max<size_t>(1, runnable.size()))) != cudaSuccess) return bail(e, "cudaMalloc order");
+        if ((e = cudaMemcpy(p->d_units, p->units.data(), sizeof(lzgpu_unit) * (size_t)n, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload units");
+        if (!runnable.empty() && (e = cudaMemcpy(p->d_order, runnable.data(), sizeof(int32_t) * runnable.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload order");
+        if ((e = cudaMemcpy(p->d_results, p->preset.data(), sizeof(lzgpu_result) * (size_t)n, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload results");
+    }
+    if (ws_slots) {
+        p->lit_ws_stride = (uint64_t)0x300 << ws_bits;
+        if ((e = cudaMalloc(&p->d_lit_ws, ws_slots * p->lit_ws_stride * 2)) != cudaSuccess) return bail(e, "cudaMalloc literal workspace");
+    }
+    if ((e = cudaEventCreate(&p->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&p->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    *out = p;
+    return LZGPU_E_OK;
+}
+
+extern "C" int lzgpu_plan_launch_count(const lzgpu_plan *p) { return p ? (int)p->launches.size() : 0; }
+
+extern "C" int lzgpu_plan_launch(lzgpu_plan *p, const uint8_t *d_in, uint8_t *d_out, void *stream) {
+    if (!p) return fail(LZGPU_E_INVALID, "plan_launch: null plan");
+    DevState &ds = p->ctx->devs[p->dev_index];
+    CUDA_TRY(cudaSetDevice(ds.device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ds.stream;
+    CUDA_TRY(cudaEventRecord(p->ev0, st));
+    for (const Launch &L : p->launches) {
+        KArgs a;
+        a.units = p->d_units;
+        a.order = p->d_order;
+        a.in_base = d_in;
+        a.out_base = d_out;
+        a.results = p->d_results;
+        a.lit_ws = p->d_lit_ws;
+        a.lit_ws_stride = p->lit_ws_stride;
+        a.lit_bits_cap = L.lit_bits;
+        a.slot0 = L.slot0;
+        if (L.lit_global) lzgpu_decode_kernel<true><<<L.count, 32, L.smem, st>>>(a);
+        else lzgpu_decode_kernel<false><<<L.count, 32, L.smem, st>>>(a);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaEventRecord(p->ev1, st));
+    p->last_stream = st;
+    p->launched = true;
+    return LZGPU_E_OK;
+}
+
+extern "C" int lzgpu_plan_results(lzgpu_plan *p, lzgpu_result *results, lzgpu_stats *stats) {
+    if (!p || !p->launched) return fail(LZGPU_E_INVALID, "plan_results: plan was not launched");
+    DevState &ds = p->ctx->devs[p->dev_index];
+    CUDA_TRY(cudaSetDevice(ds.device));
+    CUDA_TRY(cudaEventSynchronize(p->ev1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+    std::vector<lzgpu_result> tmp((size_t)p->n);
+    if (p->n) CUDA_TRY(cudaMemcpy(tmp.data(), p->d_results, sizeof(lzgpu_result) * (size_t)p->n, cudaMemcpyDeviceToHost));
+    uint64_t bi = 0, bo = 0;
+    for (int64_t i = 0; i < p->n; i++) {
+        lzgpu_result r = tmp[(size_t)i];
+        r.device = ds.device;
+        if (p->preset[(size_t)i].status != LZGPU_NOT_RUN) r = p->preset[(size_t)i];
+        else if (p->was_alone[(size_t)i]) r.bytes_in += 13;   // the .lzma header consumed on the host
+        bi += r.bytes_in;
+        bo += r.bytes_out;
+        if (results) results[i] = r;
+    }
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->kernel_ms = ms;
+        stats->bytes_in = bi;
+        stats->bytes_out = bo;
+        stats->launches = (int32_t)p->launches.size();
+        stats->devices = 1;
+    }
+    return LZGPU_E_OK;
+}
+
+// ------------------------------------------------------------------ host-buffer batch
+namespace {
+
+struct Shard {
+    std::vector<int64_t> idx;          // unit indices (caller's numbering)
+    std::vector<lzgpu_unit> units;     // rebased into the shard's device slabs
+    struct Run { uint64_t host_off, dev_off, len; };
+    std::vector<Run> in_runs, out_runs;
+    uint64_t in_bytes = 0, out_bytes = 0;
+    int rc = 0;
+    std::string err;
+    double kernel_ms = 0, h2d_ms = 0, d2h_ms = 0;
+    int launches = 0;
+};
+
+// Coalesce [off, off+len) ranges (sorted by off) into few large copies; returns the
+// device offset of each range.
+void layout_ranges(const std::vector<std::pair<uint64_t, uint64_t>> &ranges, std::vector<uint64_t> &dev_off,
+                   std::vector<Shard::Run> &runs, uint64_t &total) {
+    const size_t n = ranges.size();
+    std::vector<size_t> ord(n);
+    std::iota(ord.begin(), ord.end(), 0);
+    std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return ranges[a].first < ranges[b].first; });
+    dev_off.assign(n, 0);
+    total = 0;
+    const uint64_t kGap = 64 << 10;
+    for (size_t k = 0; k < n; k++) {
+        const auto &r = ranges[ord[k]];
+        if (!runs.empty()) {
+            Shard::Run &last = runs.back();
+            const uint64_t last_end = last.host_off + last.len;
+            if (r.first <= last_end + kGap) {
+                const uint64_t new_end = std::max(last_end, r.first + r.second);
+                dev_off[ord[k]] = last.dev_off + (r.first - last.host_off);
+                last.len = new_end - last.host_off;
+                total = last.dev_off + last.len;
+                continue;
+            }
+        }
+        // new run; keep host and device offsets congruent mod 16 so 4-byte alignment is preserved
+        uint64_t d = (total + 255) & ~(uint64_t)255;
+        d += r.first & 15;
+        runs.push_back({r.first, d, r.second});
+        dev_off[ord[k]] = d;
+        total = d + r.second;
+    }
+}
+
+int ensure(uint8_t *&ptr, uint64_t &cap, uint64_t need) {
+    if (need <= cap) return 0;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    const uint64_t want = need + (need >> 3) + 4096;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+    cap = want;
+    return 0;
+}
+
+void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base, uint8_t *out_base,
+               lzgpu_result *results) {
+    DevState &ds = ctx->devs[dev_index];
+    auto cuda_fail = [&](cudaError_t e, const char *what) {
+        sh.rc = e == cudaErrorMemoryAllocation ? LZGPU_E_NOMEM : LZGPU_E_CUDA;
+        sh.err = std::string(what) + ": " + cudaGetErrorString(e);
+    };
+    cudaError_t e = cudaSetDevice(ds.device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    const size_t n = sh.idx.size();
+    if (n == 0) return;
+    // device layout
+    std::vector<std::pair<uint64_t, uint64_t>> ir(n), orr(n);
+    for (size_t k = 0; k < n; k++) {
+        ir[k] = {sh.units[k].in_off, sh.units[k].in_len};
+        orr[k] = {sh.units[k].out_off, sh.units[k].out_cap};
+    }
+    std::vector<uint64_t> ioff, ooff;
+    layout_ranges(ir, ioff, sh.in_runs, sh.in_bytes);
+    layout_ranges(orr, ooff, sh.out_runs, sh.out_bytes);
+    for (size_t k = 0; k < n; k++) { sh.units[k].in_off = ioff[k]; sh.units[k].out_off = ooff[k]; }
+    if (ensure(ds.d_in, ds.in_cap, sh.in_bytes + 16) || ensure(ds.d_out, ds.out_cap, sh.out_bytes + 16)) {
+        sh.rc = LZGPU_E_NOMEM;
+        sh.err = "cudaMalloc of the shard's input/output slabs failed";
+        return;
+    }
+    lzgpu_plan *plan = nullptr;
+    int rc = lzgpu_plan_create(ctx, dev_index, sh.units.data(), (int64_t)n, sh.in_bytes + 16, sh.out_bytes + 16, &plan);
+    if (rc != LZGPU_E_OK) { sh.rc = rc; sh.err = g_last_error; return; }
+    cudaEvent_t e0, e1, e2, e3;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+    cudaEventRecord(e0, ds.stream);
+    for (const auto &r : sh.in_runs) {
+        e = cudaMemcpyAsync(ds.d_in + r.dev_off, in_base + r.host_off, r.len, cudaMemcpyHostToDevice, ds.stream);
+        if (e != cudaSuccess) { cuda_fail(e, "H2D"); break; }
+    }
+    cudaEventRecord(e1, ds.stream);
+    if (sh.rc == 0) {
+        rc = lzgpu_plan_launch(plan, ds.d_in, ds.d_out, ds.stream);
+        if (rc != LZGPU_E_OK) { sh.rc = rc; sh.err = g_last_error; }
+    }
+    cudaEventRecord(e2, ds.stream);
+    if (sh.rc == 0) {
+        for (const auto &r : sh.out_runs) {
+            e = cudaMemcpyAsync(out_base + r.host_off, ds.d_out + r.dev_off, r.len, cudaMemcpyDeviceToHost, ds.stream);
+            if (e != cudaSuccess) { cuda_fail(e, "D2H"); break; }
+        }
+    }
+    cudaEventRecord(e3, ds.stream);
+    e = cudaStreamSynchronize(ds.stream);
+    if (e != cudaSuccess && sh.rc == 0) cuda_fail(e, "decode kernel / stream sync");
+    if (sh.rc == 0) {
+        std::vector<lzgpu_result> tmp(n);
+        lzgpu_stats st;
+        rc = lzgpu_plan_results(plan, tmp.data(), &st);
+        if (rc != LZGPU_E_OK) { sh.rc = rc; sh.err = g_last_error; }
+        else {
+            for (size_t k = 0; k < n; k++) results[sh.idx[k]] = tmp[k];
+            sh.kernel_ms = st.kernel_ms;
+            sh.launches = st.launches;
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, e0, e1);
+            cudaEventElapsedTime(&b, e2, e3);
+            sh.h2d_ms = a;
+            sh.d2h_ms = b;
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+    lzgpu_plan_destroy(plan);
+}
+
+}  // namespace
+
+extern "C" int lzgpu_decode_batch(lzgpu_ctx *ctx, const lzgpu_unit *units, int64_t n,
+                                  const uint8_t *in_base, uint64_t in_size,
+                                  uint8_t *out_base, uint64_t out_size,
+                                  lzgpu_result *results, lzgpu_stats *stats) {
+    if (!ctx || n < 0 || (n > 0 && (!units || !results))) return fail(LZGPU_E_INVALID, "decode_batch: bad arguments");
+    if (ctx->devs.empty()) return fail(LZGPU_E_NO_DEVICE, "decode_batch: context has no device");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int64_t i = 0; i < n; i++) {
+        const lzgpu_unit &u = units[i];
+        if (u.in_off > in_size || u.in_len > in_size - u.in_off || u.out_off > out_size || u.out_cap > out_size - u.out_off)
+            return fail(LZGPU_E_INVALID, "decode_batch: unit " + std::to_string(i) + " lies outside the buffers");
+        memset(&results[i], 0, sizeof results[i]);
+        results[i].status = LZGPU_NOT_RUN;
+    }
+    const int nd = (int)ctx->devs.size();
+    std::vector<int32_t> shard_of((size_t)n);
+    int rc = lzgpu_shard_units(units, n, nd, shard_of.data());
+    if (rc != LZGPU_E_OK) return rc;
+    std::vector<Shard> shards((size_t)nd);
+    for (int64_t i = 0; i < n; i++) {
+        lzgpu_unit u = units[i];
+        if (u.kind == LZGPU_KIND_LZMA1_ALONE) {
+            // NewReader1 reads the 13-byte header eagerly (reader1.go:77-101)
+            const int hs = lzgpu_parse_alone_header(in_base + u.in_off, u.in_len, &u);
+            if (hs != LZGPU_OK) { results[i].status = hs; results[i].device = -1; continue; }
+        }
+        Shard &s = shards[(size_t)shard_of[(size_t)i]];
+        s.idx.push_back(i);
+        s.units.push_back(u);
+    }
+    if (nd == 1) {
+        run_shard(ctx, 0, shards[0], in_base, out_base, results);
+    } else {
+        std::vector<std::thread> th;
+        for (int d = 0; d < nd; d++)
+            th.emplace_back([&, d]() { run_shard(ctx, d, shards[(size_t)d], in_base, out_base, results); });
+        for (auto &t : th) t.join();
+    }
+    lzgpu_stats st;
+    memset(&st, 0, sizeof st);
+    for (int d = 0; d < nd; d++) {
+        if (shards[(size_t)d].rc != 0) return fail(shards[(size_t)d].rc, "device " + std::to_string(ctx->devs[(size_t)d].device) + ": " + shards[(size_t)d].err);
+        st.kernel_ms = std::max(st.kernel_ms, shards[(size_t)d].kernel_ms);
+        st.h2d_ms = std::max(st.h2d_ms, shards[(size_t)d].h2d_ms);
+        st.d2h_ms = std::max(st.d2h_ms, shards[(size_t)d].d2h_ms);
+        st.launches += shards[(size_t)d].launches;
+    }
+    for (int64_t i = 0; i < n; i++) {
+        st.bytes_in += results[i].bytes_in;
+        st.bytes_out += results[i].bytes_out;
+    }
+    st.devices = nd;
+    st.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (stats) *stats = st;
+    return LZGPU_E_OK;
+}

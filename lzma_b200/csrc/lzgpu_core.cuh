@@ -1,0 +1,372 @@
+// lzgpu_core.cuh -- the in-stream LZMA symbol decoder that lane 0 of each warp runs,
+// plus the per-lane phases of the warp-cooperative window copy.
+//
+// Follows (restated, not translated) the reference's live hot loop
+// (*Reader1).decompress, decompress.go:8-1136, whose hand-inlined bit steps are the
+// twins range_decoder.go:57-134, bit_tree_decoder.go:26-135, len_decoder.go:34-60,
+// reader1.go:256-426; the 12-state machine state.go:153-187; window semantics
+// window.go:31-95.  The ORDER of the size / EOS / distance checks is the
+// reference's, because it decides which error a malformed stream reports.
+//
+// Differences in mechanism (results are identical):
+//  * the output buffer in HBM *is* the dictionary window: there is no circular
+//    buffer and no second ReadPending copy (window.go:101-133);
+//  * match copies are executed by all 32 lanes and their stores are deferred
+//    until the next copy, so the serial decoder never waits for a window load
+//    unless the very next symbol is a literal that needs its context bytes;
+//  * probability tables live in shared memory in our own layout (P_* below).
+//
+// The file compiles for the device (nvcc) and, with the LZ_HD macros degrading to
+// plain inline functions, for the host lane-emulation harness under tests/emu/
+// (test infrastructure; never linked into liblzgpu.so).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/lzgpu.h"
+
+#if defined(__CUDACC__)
+#define LZ_HD __host__ __device__ __forceinline__
+#else
+#define LZ_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define LZ_LD_IN8(p) __ldg(reinterpret_cast<const unsigned char *>(p))
+#define LZ_LD_IN32(p) __ldg(reinterpret_cast<const unsigned int *>(p))
+#define LZ_BSWAP32(x) __byte_perm((x), 0u, 0x0123u)
+#define LZ_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#define LZ_LIKELY(x) __builtin_expect(!!(x), 1)
+#define LZ_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#define LZ_LD_IN8(p) (*(const uint8_t *)(p))
+#define LZ_LD_IN32(p) (*(const uint32_t *)(p))
+#define LZ_BSWAP32(x) __builtin_bswap32(x)
+#define LZ_PREFETCH_L2(p) ((void)0)
+#define LZ_LIKELY(x) __builtin_expect(!!(x), 1)
+#define LZ_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#endif
+
+namespace lzgpu {
+
+// ---- probability-table layout, in uint16 units (Appendix A of SURVEY.md lists the
+// reference's tables: state.go:3-33).  isRep/G0/G1/G2 are interleaved per state.
+enum : uint32_t {
+    P_IS_MATCH = 0,        // [12][16]  (state<<4)+posState        decompress.go:23,26
+    P_IS_REP0_LONG = 192,  // [12][16]                              decompress.go:716
+    P_REP4 = 384,          // [12][4]   isRep, isRepG0, isRepG1, isRepG2 of one state
+    P_LEN0 = 432,          // match length coder (LEN_* below)      decompress.go:218-429
+    P_LEN1 = 952,          // rep length coder                      decompress.go:870-1118
+    P_POS_SLOT = 1472,     // [4][64]                               decompress.go:434-486
+    P_POS_DEC = 1728,      // [115] (+13 pad)                       decompress.go:491-546
+    P_ALIGN = 1856,        // [16]                                  decompress.go:580-625
+    P_LIT = 1872,          // 0x300 << (lc+lp)                      decompress.go:56-57
+    P_FIXED = 1872
+};
+enum : uint32_t { LEN_CHOICE = 0, LEN_CHOICE2 = 1, LEN_LOW = 8, LEN_MID = 136, LEN_HIGH = 264, LEN_SIZE = 520 };
+
+constexpr uint32_t kTop = 1u << 24;
+constexpr uint32_t kProbInit = 1024;
+
+// what lane 0 hands to the warp when it leaves decode_run()
+enum : uint32_t { OP_COPY = 0, OP_COPY_Q4 = 1, OP_DONE = 2 };
+
+// Lane 0's decoder registers.
+struct Dec {
+    uint32_t range, code;
+    uint32_t inbuf, incnt;          // next input bytes, most significant first
+    const uint8_t *ip, *in_end;
+    uint32_t rep0, rep1, rep2, rep3, state;
+    uint32_t wpos, dict_size;       // window.pos (wrapped, Q3) and window.size
+    uint32_t full;                  // window.isFull
+    uint8_t *outp, *out_end;        // write cursor; out_end = start + min(size, cap)
+    uint32_t end_is_size;           // out_end is the declared unpack size (else the caller's cap)
+    uint32_t size_defined;          // state.unpackSizeDefined
+    uint32_t lc, lp_mask, pos_mask;
+    uint32_t prev_byte, mbyte;      // literal context: byte at -1 and at -(rep0+1)
+    int32_t status, site;
+};
+
+LZ_HD bool rc_refill(Dec &d) {
+    const uint64_t rem = (uint64_t)(d.in_end - d.ip);
+    if (rem == 0) return false;
+    const uint32_t mis = (uint32_t)((uintptr_t)d.ip & 3u);
+    if (LZ_LIKELY(mis == 0 && rem >= 4)) {
+        d.inbuf = LZ_BSWAP32(LZ_LD_IN32(d.ip));
+        d.incnt = 4;
+        d.ip += 4;
+        if (((uintptr_t)d.ip & 127u) == 0) LZ_PREFETCH_L2(d.ip + 256);
+    } else {
+        uint32_t n = 4 - mis;
+        if (n > rem) n = (uint32_t)rem;
+        uint32_t w = 0;
+        for (uint32_t i = 0; i < n; i++) w |= (uint32_t)LZ_LD_IN8(d.ip + i) << (24 - 8 * i);
+        d.inbuf = w;
+        d.incnt = n;
+        d.ip += n;
+    }
+    return true;
+}
+
+// Range-coder preamble: rangeDecoder.Init, range_decoder.go:27-46.
+// 0 ok, 1 first byte != 0, -1 fewer than 5 bytes.
+LZ_HD int rc_init(Dec &d) {
+    d.range = 0xFFFFFFFFu;
+    d.code = 0;
+    d.inbuf = 0;
+    d.incnt = 0;
+    if ((uint64_t)(d.in_end - d.ip) < 1) return -1;
+    if (LZ_LD_IN8(d.ip) != 0) return 1;
+    if ((uint64_t)(d.in_end - d.ip) < 5) { d.ip = d.in_end; return -1; }
+    uint32_t c = 0;
+    for (int i = 1; i < 5; i++) c = (c << 8) | LZ_LD_IN8(d.ip + i);
+    d.code = c;
+    d.ip += 5;
+    return 0;
+}
+
+// One adaptive bit (DecodeBit, range_decoder.go:57-98) with the reference's
+// normalise-after-the-bit order.  On input exhaustion jumps to input_eof.
+#define LZ_NORM()                                                         \
+    do {                                                                  \
+        if (d.range < kTop) {                                             \
+            if (LZ_UNLIKELY(d.incnt == 0)) {                              \
+                if (!rc_refill(d)) goto input_eof;                        \
+            }                                                             \
+            d.range <<= 8;                                                \
+            d.code = (d.code << 8) | (d.inbuf >> 24);                     \
+            d.inbuf <<= 8;                                                \
+            d.incnt--;                                                    \
+        }                                                                 \
+    } while (0)
+
+#define LZ_BIT(PP, BIT)                                                   \
+    do {                                                                  \
+        uint16_t *pp_ = (PP);                                             \
+        const uint32_t p_ = *pp_;                                         \
+        const uint32_t bound_ = (d.range >> 11) * p_;                     \
+        if (d.code < bound_) {                                            \
+            d.range = bound_;                                             \
+            *pp_ = (uint16_t)(p_ + ((2048u - p_) >> 5));                  \
+            (BIT) = 0;                                                    \
+        } else {                                                          \
+            d.range -= bound_;                                            \
+            d.code -= bound_;                                             \
+            *pp_ = (uint16_t)(p_ - (p_ >> 5));                            \
+            (BIT) = 1;                                                    \
+        }                                                                 \
+        LZ_NORM();                                                        \
+    } while (0)
+
+// MSB-first bit tree (BitTreeDecode, bit_tree_decoder.go:26-76)
+#define LZ_TREE(PROBS, NBITS, OUT)                                        \
+    do {                                                                  \
+        uint16_t *tp_ = (PROBS);                                          \
+        uint32_t m_ = 1, b_;                                              \
+        for (int i_ = 0; i_ < (NBITS); i_++) {                            \
+            LZ_BIT(tp_ + m_, b_);                                         \
+            m_ = (m_ << 1) | b_;                                          \
+        }                                                                 \
+        (OUT) = m_ - (1u << (NBITS));                                     \
+    } while (0)
+
+// LSB-first bit tree (BitTreeReverseDecode, bit_tree_decoder.go:82-135)
+#define LZ_TREE_REV(PROBS, NBITS, OUT)                                    \
+    do {                                                                  \
+        uint16_t *tp_ = (PROBS);                                          \
+        uint32_t m_ = 1, b_, s_ = 0;                                      \
+        for (uint32_t i_ = 0; i_ < (uint32_t)(NBITS); i_++) {             \
+            LZ_BIT(tp_ + m_, b_);                                         \
+            m_ = (m_ << 1) | b_;                                          \
+            s_ |= b_ << i_;                                               \
+        }                                                                 \
+        (OUT) = s_;                                                       \
+    } while (0)
+
+// lenDecoder.Decode (len_decoder.go:34-60); WHICH = 0 low, 1 mid, 2 high
+#define LZ_LEN(LP, POS_STATE, LEN, WHICH)                                 \
+    do {                                                                  \
+        uint16_t *lp_ = (LP);                                             \
+        uint32_t lb_, lv_;                                                \
+        LZ_BIT(lp_ + LEN_CHOICE, lb_);                                    \
+        if (lb_ == 0) {                                                   \
+            LZ_TREE(lp_ + LEN_LOW + ((POS_STATE) << 3), 3, lv_);          \
+            (LEN) = lv_; (WHICH) = 0;                                     \
+        } else {                                                          \
+            LZ_BIT(lp_ + LEN_CHOICE2, lb_);                               \
+            if (lb_ == 0) {                                               \
+                LZ_TREE(lp_ + LEN_MID + ((POS_STATE) << 3), 3, lv_);      \
+                (LEN) = 8 + lv_; (WHICH) = 1;                             \
+            } else {                                                      \
+                LZ_TREE(lp_ + LEN_HIGH, 8, lv_);                          \
+                (LEN) = 16 + lv_; (WHICH) = 2;                            \
+            }                                                             \
+        }                                                                 \
+    } while (0)
+
+#define LZ_FAIL(ST, SITE)                                                 \
+    do { d.status = (ST); d.site = (SITE); return OP_DONE; } while (0)
+
+// Runs lane 0's serial decoder until a symbol needs the warp (a match / rep /
+// short rep: OP_COPY or OP_COPY_Q4 with len and dist set, window position already
+// advanced) or the unit part ends (OP_DONE with d.status / d.site set).
+// P: fixed tables (shared memory), L: literal tables (shared or global).
+LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, uint32_t &out_dist) {
+    for (;;) {
+        const bool at_end = (d.outp == d.out_end);
+        // decompress.go:14-20
+        if (at_end && d.end_is_size && d.code == 0) LZ_FAIL(LZGPU_OK, 0);
+
+        const uint32_t pos_state = d.wpos & d.pos_mask;          // :22
+        const uint32_t state2 = (d.state << 4) + pos_state;      // :23
+        uint32_t bit;
+        LZ_BIT(P + P_IS_MATCH + state2, bit);                    // :25-42
+
+        if (bit == 0) {  // literal, :44-175
+            if (at_end) {
+                if (d.end_is_size) LZ_FAIL(LZGPU_RESULT_ERROR, 46);
+                LZ_FAIL(LZGPU_OUTPUT_OVERFLOW, 0);
+            }
+            uint16_t *pr = L + 0x300u * (((d.wpos & d.lp_mask) << d.lc) + (d.prev_byte >> (8 - d.lc)));  // :56-57
+            uint32_t sym = 1;
+            if (d.state >= 7) {  // matched literal, :59-114
+                uint32_t mb = d.mbyte;
+                do {
+                    const uint32_t mbit = (mb >> 7) & 1;
+                    mb <<= 1;
+                    LZ_BIT(pr + ((1 + mbit) << 8) + sym, bit);
+                    sym = (sym << 1) | bit;
+                    if (mbit != bit) break;
+                } while (sym < 0x100);
+            }
+            while (sym < 0x100) {  // :127-166
+                LZ_BIT(pr + sym, bit);
+                sym = (sym << 1) | bit;
+            }
+            sym &= 0xFF;
+            *d.outp++ = (uint8_t)sym;                             // PutByte, :168
+            d.prev_byte = sym;
+            if (++d.wpos >= d.dict_size) { d.wpos -= d.dict_size; d.full = 1; }
+            d.state = d.state < 4 ? 0 : (d.state < 10 ? d.state - 3 : d.state - 6);  // stateUpdateLiteral
+            continue;
+        }
+
+        uint32_t len, which = 0, trunc_site;
+        uint16_t *rep4 = P + P_REP4 + (d.state << 2);
+        LZ_BIT(rep4 + 0, bit);                                    // isRep, :195-213
+        if (bit == 0) {  // simple match, :215-668
+            d.rep3 = d.rep2; d.rep2 = d.rep1; d.rep1 = d.rep0;    // :216
+            LZ_LEN(P + P_LEN0, pos_state, len, which);            // :218-429
+            d.state = d.state < 7 ? 7 : 10;                       // stateUpdateMatch, :431
+            const uint32_t len_state = len > 3 ? 3 : len;         // :434-437
+            uint32_t slot;
+            LZ_TREE(P + P_POS_SLOT + (len_state << 6), 6, slot);  // :441-486
+            if (slot < 4) {
+                d.rep0 = slot;                                    // :488-489
+            } else {
+                const uint32_t nd = (slot >> 1) - 1;
+                uint32_t dist = (2 | (slot & 1)) << nd, v;
+                if (slot < 14) {                                  // :494-546
+                    LZ_TREE_REV(P + P_POS_DEC + dist - slot, nd, v);
+                    dist += v;
+                } else {                                          // :548-628
+                    uint32_t res = 0;
+                    for (uint32_t n = nd - 4; n > 0; n--) {       // DecodeDirectBits, :549-576
+                        d.range >>= 1;
+                        d.code -= d.range;
+                        const uint32_t t = 0u - (d.code >> 31);
+                        d.code += d.range & t;
+                        res = (res << 1) + (t + 1);
+                        LZ_NORM();
+                    }
+                    dist += res << 4;
+                    LZ_TREE_REV(P + P_ALIGN, 4, v);               // :580-625
+                    dist += v;
+                }
+                d.rep0 = dist;
+            }
+            if (d.rep0 == 0xFFFFFFFFu) {                          // EOS marker, :633-645
+                if (d.code == 0) {
+                    // sizeDefined && bytesLeft > 0 (a cap below the declared size implies bytes left)
+                    if (d.size_defined && !(d.end_is_size && at_end)) LZ_FAIL(LZGPU_RESULT_ERROR, 636);
+                    LZ_FAIL(LZGPU_OK, 0);
+                }
+                LZ_FAIL(LZGPU_RESULT_ERROR, 643);
+            }
+            if (at_end) {                                         // :647-649
+                if (d.end_is_size) LZ_FAIL(LZGPU_RESULT_ERROR, 648);
+                LZ_FAIL(LZGPU_OUTPUT_OVERFLOW, 0);
+            }
+            if (d.rep0 >= d.dict_size || !(d.full || d.rep0 <= d.wpos))  // :651-653 (Q4 as written)
+                LZ_FAIL(LZGPU_RESULT_ERROR, 652);
+            len += 2;                                             // :656
+            trunc_site = 662;
+        } else {  // rep match, :685-1118
+            if (at_end) {                                         // :686-688
+                if (d.end_is_size) LZ_FAIL(LZGPU_RESULT_ERROR, 687);
+                LZ_FAIL(LZGPU_OUTPUT_OVERFLOW, 0);
+            }
+            if (d.wpos == 0 && !d.full) LZ_FAIL(LZGPU_RESULT_ERROR, 691);  // IsEmpty, :690-692
+            bool short_rep = false;
+            LZ_BIT(rep4 + 1, bit);                                // isRepG0, :694-772
+            if (bit == 0) {
+                LZ_BIT(P + P_IS_REP0_LONG + state2, bit);         // :715-755
+                short_rep = (bit == 0);
+            } else {
+                uint32_t dist;
+                LZ_BIT(rep4 + 2, bit);                            // isRepG1, :777-813
+                if (bit == 0) {
+                    dist = d.rep1; d.rep1 = d.rep0; d.rep0 = dist;
+                } else {
+                    LZ_BIT(rep4 + 3, bit);                        // isRepG2, :816-861
+                    if (bit == 0) { dist = d.rep2; d.rep2 = d.rep1; d.rep1 = d.rep0; d.rep0 = dist; }
+                    else { dist = d.rep3; d.rep3 = d.rep2; d.rep2 = d.rep1; d.rep1 = d.rep0; d.rep0 = dist; }
+                }
+            }
+            if (short_rep) {                                      // :735-739
+                d.state = d.state < 7 ? 9 : 11;                   // stateUpdateShortRep
+                len = 1;
+                trunc_site = 0;
+            } else {
+                LZ_LEN(P + P_LEN1, pos_state, len, which);        // :870-1101
+                d.state = d.state < 7 ? 8 : 11;                   // stateUpdateRep
+                len += 2;
+                trunc_site = which == 0 ? 941 : (which == 1 ? 1035 : 1111);
+            }
+        }
+
+        // copy: decompress.go:656-668 / :934-947 / :1028-1041 / :1104-1117
+        const uint64_t avail = (uint64_t)(d.out_end - d.outp);
+        if (d.end_is_size) {
+            if ((uint32_t)avail < len) LZ_FAIL(LZGPU_RESULT_ERROR, trunc_site);  // uint32(bytesLeft) < length (Q10)
+        } else if (avail < len) {
+            LZ_FAIL(LZGPU_OUTPUT_OVERFLOW, 0);
+        }
+        const uint32_t dist = d.rep0 + 1;
+        uint32_t op = OP_COPY;
+        if (LZ_UNLIKELY(!d.full && dist > d.wpos)) {
+            // Fewer than `dist` bytes since the dictionary start.  dist == wpos+1 is the
+            // reference's off-by-one (Q4): the byte before the start reads as 0 in a fresh
+            // window.  Anything further can only come from a rep after an LZMA2 dictionary
+            // reset without state reset (Q5): bounds-checked here, a documented deviation.
+            if (dist != d.wpos + 1) LZ_FAIL(LZGPU_RESULT_ERROR, LZGPU_SITE_REP_BEFORE_DICT);
+            op = OP_COPY_Q4;
+        }
+        d.wpos += len;
+        if (d.wpos >= d.dict_size) { d.wpos -= d.dict_size; d.full = 1; }
+        out_len = len;
+        out_dist = dist;
+        return op;
+    }
+input_eof:
+    d.status = LZGPU_OK_INPUT_EXHAUSTED;
+    d.site = 0;
+    return OP_DONE;
+}
+
+// ---- per-lane phases of the warp-cooperative window copy (window.CopyMatch,
+// window.go:55-87: byte-serial semantics, overlap replicates with period dist).
+// Byte i of a match comes from dst[src_index(i) - dist]; src_index(i) < dist always,
+// so every source byte predates the match: loads never depend on this match's stores.
+LZ_HD uint32_t src_index(uint32_t i, uint32_t dist) { return i < dist ? i : i % dist; }
+
+}  // namespace lzgpu

@@ -1,0 +1,404 @@
+// lzgpu_unit.cuh -- one warp decodes one unit.
+//
+// Written once in "warp-uniform" style and compiled two ways:
+//   * device (nvcc): the 32 lanes of a warp execute it together; lane 0 runs the
+//     serial range decoder, all lanes copy;
+//   * host lane emulation (tests/emu/, test infrastructure only): LZ_FOR_LANES
+//     loops over 32 virtual lanes and per-lane variables become arrays, so the
+//     protocol (deferred stores, what lane 0 may read when) can be checked
+//     bit-exactly on a machine with no GPU.
+//
+// Reference behaviour reproduced here: Reader1.initialize + Read loop
+// (reader1.go:149-159, 223-254) for LZMA1 units; Reader2.startChunk / Read /
+// uncompressedRead (reader2.go:100-294) for LZMA2 groups.
+#pragma once
+#include "lzgpu_core.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define LZ_LANE() (threadIdx.x & 31u)
+#define LZ_FOR_LANES(l) for (uint32_t l = LZ_LANE(), once_ = 1; once_; once_ = 0)
+#define LZ_IF_LANE0 if (LZ_LANE() == 0)
+#define LZ_SYNC() __syncwarp()
+#define LZ_BCAST32(x) ((x) = __shfl_sync(0xffffffffu, (x), 0))
+#define LZ_BCAST64(x) ((x) = __shfl_sync(0xffffffffu, (x), 0))
+#define LZ_LANEVAR(T, name) T name
+#define LZ_LV(name, l) name
+#define LZ_DEV __device__ __forceinline__
+#else
+#define LZ_FOR_LANES(l) for (uint32_t l = 0; l < 32; l++)
+#define LZ_IF_LANE0
+#define LZ_SYNC() ((void)0)
+#define LZ_BCAST32(x) ((void)0)
+#define LZ_BCAST64(x) ((void)0)
+#define LZ_LANEVAR(T, name) T name[32]
+#define LZ_LV(name, l) name[l]
+#define LZ_DEV inline
+#endif
+
+namespace lzgpu {
+
+// Uniform (same in every lane) copy bookkeeping + the per-lane deferred byte.
+struct WarpCopy {
+    uint32_t pend_len;   // bytes loaded but not yet stored (0..32)
+    uint8_t *pend_dst;
+    LZ_LANEVAR(uint8_t, pend_val);
+};
+
+LZ_DEV void wc_commit(WarpCopy &wc) {
+    LZ_FOR_LANES(l) {
+        if (l < wc.pend_len) wc.pend_dst[l] = LZ_LV(wc.pend_val, l);
+    }
+    wc.pend_len = 0;
+    LZ_SYNC();
+}
+
+LZ_DEV void probs_fill(uint16_t *p, uint32_t n) {  // initProbs, prob.go:3-7
+    LZ_FOR_LANES(l) {
+        for (uint32_t i = l; i < n; i += 32) p[i] = (uint16_t)kProbInit;
+    }
+}
+
+// state.Reset (state.go:79-121): every table back to 1024, rep0..3 = 0, state = 0.
+LZ_DEV void coder_reset(Dec &d, uint16_t *P, uint16_t *L, uint32_t lit_bits) {
+    probs_fill(P, P_FIXED);
+    probs_fill(L, 0x300u << lit_bits);
+    d.rep0 = d.rep1 = d.rep2 = d.rep3 = 0;
+    d.state = 0;
+    LZ_SYNC();
+}
+
+LZ_DEV void set_props(Dec &d, uint32_t lc, uint32_t lp, uint32_t pb) {
+    d.lc = lc;
+    d.lp_mask = (1u << lp) - 1;
+    d.pos_mask = (1u << pb) - 1;
+}
+
+// Decode symbols until the range-coded part ends (Reader1.Read driving
+// decompress(), reader1.go:223-254).  On return d.status / d.site are set and no
+// store is pending.
+LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8_t *dict_base) {
+    for (;;) {
+        uint32_t op = OP_DONE, len = 0, dist = 0;
+        uint64_t dstbits = 0;
+        LZ_IF_LANE0 {
+            op = decode_run(d, P, L, len, dist);
+            dstbits = (uint64_t)(uintptr_t)d.outp;
+        }
+        LZ_SYNC();
+        uint32_t pk = op | (len << 2);
+        LZ_BCAST32(pk);
+        op = pk & 3u;
+        len = pk >> 2;
+        if (op == OP_DONE) break;
+        LZ_BCAST32(dist);
+        LZ_BCAST64(dstbits);
+        uint8_t *dst = (uint8_t *)(uintptr_t)dstbits;
+
+        wc_commit(wc);  // the previous match's bytes reach memory before anything reads them
+
+        if (op == OP_COPY) {
+            if (len <= 32) {
+                // deferred: load now, store at the next commit
+                LZ_FOR_LANES(l) {
+                    if (l < len) LZ_LV(wc.pend_val, l) = dst[(int64_t)src_index(l, dist) - (int64_t)dist];
+                }
+                wc.pend_len = len;
+                wc.pend_dst = dst;
+            } else {
+                LZ_FOR_LANES(l) {
+                    for (uint32_t i = l; i < len; i += 32) {
+                        const uint8_t v = dst[(int64_t)src_index(i, dist) - (int64_t)dist];
+                        dst[i] = v;
+                    }
+                }
+            }
+            LZ_IF_LANE0 {
+                // context for a literal / short rep that may follow: the last byte of the
+                // match and the byte at -(rep0+1) after it.  Both predate the match.
+                d.prev_byte = dst[(int64_t)src_index(len - 1, dist) - (int64_t)dist];
+                d.mbyte = dst[(int64_t)src_index(len, dist) - (int64_t)dist];
+                d.outp = dst + len;
+            }
+        } else {  // OP_COPY_Q4: dist == bytes since dictionary start + 1; byte "-1" reads as 0
+            LZ_IF_LANE0 {
+                for (uint32_t i = 0; i < len; i++) {
+                    const uint8_t *src = dst + i - dist;
+                    dst[i] = src < dict_base ? (uint8_t)0 : *src;
+                }
+                d.prev_byte = dst[len - 1];
+                const uint8_t *m = dst + len - dist;
+                d.mbyte = m < dict_base ? (uint8_t)0 : *m;
+                d.outp = dst + len;
+            }
+            LZ_SYNC();
+        }
+    }
+    wc_commit(wc);
+}
+
+// Reload the literal context from memory (window.GetByte(1) / GetByte(rep0+1),
+// decompress.go:50-60) when the decoder (re)starts at a position it did not write.
+LZ_DEV void reload_context(Dec &d, const uint8_t *dict_base) {
+    LZ_IF_LANE0 {
+        const uint64_t hist = (uint64_t)(d.outp - dict_base);
+        d.prev_byte = hist > 0 ? d.outp[-1] : 0;
+        d.mbyte = ((uint64_t)d.rep0 + 1 <= hist) ? d.outp[-(int64_t)((uint64_t)d.rep0 + 1)] : 0;
+    }
+}
+
+struct UnitIO {
+    const uint8_t *in;       // unit's compressed bytes
+    uint64_t in_len;
+    uint8_t *out;            // unit's output
+    uint64_t out_cap;
+};
+
+// LZMA1 unit (kind RAW; ALONE units are converted by the host).
+LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, uint16_t *L,
+                           lzgpu_result &res) {
+    Dec d;
+    WarpCopy wc;
+    wc.pend_len = 0;
+    wc.pend_dst = io.out;
+    set_props(d, u.lc, u.lp, u.pb);
+    d.dict_size = u.dict_size;
+    d.wpos = 0;
+    d.full = 0;
+    d.prev_byte = 0;
+    d.mbyte = 0;
+    d.outp = io.out;
+    d.size_defined = u.unpack_size != LZGPU_UNKNOWN_SIZE;   // state.go:135-151
+    d.end_is_size = d.size_defined && u.unpack_size <= io.out_cap;
+    d.out_end = io.out + (d.end_is_size ? u.unpack_size : io.out_cap);
+    d.ip = io.in;
+    d.in_end = io.in + io.in_len;
+    d.status = LZGPU_OK;
+    d.site = 0;
+    coder_reset(d, P, L, (uint32_t)u.lc + u.lp);
+
+    int32_t r = 0;
+    LZ_IF_LANE0 { r = rc_init(d); }
+    LZ_BCAST32(r);
+    if (r < 0) { d.status = LZGPU_UNEXPECTED_EOF; }                       // "rangeDec.Init: %w" of io.EOF
+    else if (r > 0) { d.status = LZGPU_RESULT_ERROR; d.site = LZGPU_SITE_RC_INIT; }
+    else run_lzma(d, wc, P, L, io.out);
+
+    LZ_IF_LANE0 {
+        res.status = d.status;
+        res.err_site = d.site;
+        res.bytes_out = (uint64_t)(d.outp - io.out);
+        res.bytes_in = (uint64_t)(d.ip - io.in) - d.incnt;
+        res.final_code = d.code;
+    }
+}
+
+// LZMA2 group: walk the chunks (Reader2.startChunk + Read, reader2.go:100-250).
+LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, uint16_t *L,
+                           uint32_t lit_bits_cap, lzgpu_result &res) {
+    Dec d;
+    WarpCopy wc;
+    wc.pend_len = 0;
+    wc.pend_dst = io.out;
+    set_props(d, u.lc, u.lp, u.pb);
+    d.dict_size = u.dict_size;
+    d.wpos = 0;
+    d.full = 0;
+    d.prev_byte = 0;
+    d.mbyte = 0;
+    d.rep0 = d.rep1 = d.rep2 = d.rep3 = 0;
+    d.state = 0;
+    d.range = 0xFFFFFFFFu;
+    d.code = 0;
+    d.inbuf = 0;
+    d.incnt = 0;
+    d.outp = io.out;
+    d.out_end = io.out;
+    d.end_is_size = 1;
+    d.size_defined = 1;
+    d.status = LZGPU_OK;
+    d.site = 0;
+
+    const uint8_t *ip = io.in;                 // chunk cursor (uniform)
+    const uint8_t *const in_end = io.in + io.in_len;
+    uint8_t *const out_limit = io.out + io.out_cap;
+    const uint8_t *dict_base = io.out;         // window.Reset() moves it (window.go:135-140)
+    uint32_t have_coder = 0;                   // r.lzmaReader != nil, for this unit
+    uint32_t props = ((uint32_t)u.pb * 5 + u.lp) * 9 + u.lc;  // r.header[5]: persists between chunks (Q8)
+    int32_t status = LZGPU_OK, site = 0;
+    uint64_t consumed = 0;
+
+    for (;;) {
+        // ---- startChunk: lane 0 reads the header, everybody gets the verdict ----
+        uint32_t ctrl = 0, hdr = 0;  // hdr: [0]=end [1]=eof ; usz, csz below
+        uint32_t usz = 0, csz = 0, newprops = 0xFFFFFFFFu;
+        LZ_IF_LANE0 {
+            const uint64_t rem = (uint64_t)(in_end - ip);
+            if (rem == 0) {
+                hdr = 2;  // ran off the unit: fine between units, UnexpectedEOF at the stream's end
+            } else {
+                ctrl = LZ_LD_IN8(ip);
+                if (ctrl == 0 || (ctrl >= 3 && ctrl < 0x80)) {
+                    hdr = 1;  // end of stream; 0x03..0x7F too (Q6, reader2.go:185-198)
+                } else {
+                    const uint32_t hl = ctrl < 0x80 ? 3 : (ctrl < 0xC0 ? 5 : 6);   // chunkLength, :201-214
+                    if (rem < hl) {
+                        hdr = 3;  // truncated header -> io.ErrUnexpectedEOF (:121-128)
+                    } else {
+                        usz = ((uint32_t)LZ_LD_IN8(ip + 1) << 8) | LZ_LD_IN8(ip + 2);          // :130
+                        if (ctrl >= 0x80) {
+                            usz |= (ctrl & 0x1Fu) << 16;                                        // :141
+                            csz = (((uint32_t)LZ_LD_IN8(ip + 3) << 8) | LZ_LD_IN8(ip + 4)) + 1; // :143-144 (no uint16 wrap: Q7)
+                            if (ctrl >= 0xC0) newprops = LZ_LD_IN8(ip + 5);
+                        }
+                        usz += 1;
+                    }
+                }
+            }
+        }
+        LZ_BCAST32(hdr);
+        if (hdr != 0) {
+            if (hdr == 1) { consumed = (uint64_t)(ip - io.in) + 1; status = LZGPU_OK; }
+            else {
+                consumed = hdr == 3 ? io.in_len : (uint64_t)(ip - io.in);
+                status = (hdr == 3 || (u.flags & LZGPU_UF_LZMA2_LAST)) ? LZGPU_UNEXPECTED_EOF : LZGPU_OK;
+            }
+            break;
+        }
+        LZ_BCAST32(ctrl);
+        LZ_BCAST32(usz);
+        LZ_BCAST32(csz);
+        LZ_BCAST32(newprops);
+        const uint32_t hl = ctrl < 0x80 ? 3 : (ctrl < 0xC0 ? 5 : 6);
+        const uint8_t *payload = ip + hl;
+        if (newprops != 0xFFFFFFFFu) props = newprops;
+
+        if (ctrl == 1 || ctrl >= 0xE0) {  // dictionary reset (:132-134)
+            dict_base = d.outp;
+            d.wpos = 0;
+            d.full = 0;
+        }
+
+        if (ctrl < 0x80) {  // ---- uncompressed chunk: uncompressedRead (:252-294) ----
+            uint64_t n = (uint64_t)(in_end - payload);
+            const bool short_payload = n < usz;
+            if (!short_payload) n = usz;
+            if ((uint64_t)(out_limit - d.outp) < n) { status = LZGPU_OUTPUT_OVERFLOW; consumed = (uint64_t)(payload - io.in); break; }
+            uint8_t *dst = d.outp;
+            LZ_FOR_LANES(l) {
+                for (uint64_t i = l; i < n; i += 32) dst[i] = LZ_LD_IN8(payload + i);
+            }
+            LZ_SYNC();
+            d.outp = dst + n;
+            uint64_t wp = (uint64_t)d.wpos + n;      // window.ReadFrom, window.go:142-155
+            while (wp >= d.dict_size) { wp -= d.dict_size; d.full = 1; }
+            d.wpos = (uint32_t)wp;
+            ip = payload + n;
+            if (short_payload) {  // the next header read hits EOF (:103-110)
+                status = LZGPU_UNEXPECTED_EOF; consumed = io.in_len; break;
+            }
+            continue;
+        }
+
+        // ---- LZMA chunk ----
+        if (!have_coder) {
+            // First LZMA chunk of the unit.  At the start of a stream the reference builds
+            // a new coder from header[5] whatever the control byte (reader2.go:146-153).
+            // Elsewhere the scanner only cuts units where the chunk resets the state.
+            if (!(u.flags & LZGPU_UF_LZMA2_FRESH) && ctrl < 0xA0) {
+                status = LZGPU_RESULT_ERROR; site = LZGPU_SITE_LZMA2_NO_STATE; consumed = (uint64_t)(ip - io.in); break;
+            }
+        }
+        if (!have_coder || ctrl >= 0xA0) {
+            if (!have_coder || ctrl >= 0xC0) {      // DecodeProp(header[5]) + Renew (:158-165)
+                if (props >= 225) { status = LZGPU_INCORRECT_PROPERTIES; consumed = (uint64_t)(ip - io.in); break; }
+                const uint32_t lc = props % 9, r = props / 9, pb = r / 5, lp = r % 5;
+                if (lc + lp > lit_bits_cap) { status = LZGPU_RESULT_ERROR; site = LZGPU_SITE_LZMA2_PROPS; consumed = (uint64_t)(ip - io.in); break; }
+                set_props(d, lc, lp, pb);
+            }
+            uint32_t lb = d.lc, m = d.lp_mask;
+            while (m) { lb++; m >>= 1; }
+            coder_reset(d, P, L, lb);                // s.Reset() (:156-157) / newState
+            have_coder = 1;
+        }
+        const uint64_t in_rem = (uint64_t)(in_end - payload);
+        const bool short_payload = in_rem < csz;
+        d.ip = payload;
+        d.in_end = payload + (short_payload ? in_rem : (uint64_t)csz);   // limitByteReader(in, cs)
+        const uint64_t cap_left = (uint64_t)(out_limit - d.outp);
+        d.size_defined = 1;                          // Reopen -> SetUnpackSize(us) (reader1.go:166-176)
+        d.end_is_size = usz <= cap_left;
+        d.out_end = d.outp + (d.end_is_size ? (uint64_t)usz : cap_left);
+        d.status = LZGPU_OK;
+        d.site = 0;
+        int32_t r = 0;
+        LZ_IF_LANE0 { r = rc_init(d); }
+        LZ_BCAST32(r);
+        if (r != 0) {
+            consumed = (uint64_t)(payload - io.in);
+            if (r < 0) { status = LZGPU_UNEXPECTED_EOF; consumed = io.in_len; }
+            else { status = LZGPU_RESULT_ERROR; site = LZGPU_SITE_RC_INIT; }
+            break;
+        }
+        reload_context(d, dict_base);
+        run_lzma(d, wc, P, L, dict_base);
+
+        // what the chunk did, as seen by every lane
+        uint32_t st = (uint32_t)d.status, st_site = (uint32_t)d.site, complete = 0, exact = 0;
+        uint64_t outbits = 0;
+        LZ_IF_LANE0 {
+            complete = d.outp == d.out_end && d.end_is_size;
+            exact = (d.ip - d.incnt) == d.in_end;
+            outbits = (uint64_t)(uintptr_t)d.outp;
+        }
+        LZ_BCAST32(st);
+        LZ_BCAST32(st_site);
+        LZ_BCAST32(complete);
+        LZ_BCAST32(exact);
+        LZ_BCAST64(outbits);
+        d.outp = (uint8_t *)(uintptr_t)outbits;
+        // keep the uniform window position in step with lane 0's
+        uint32_t wpos = d.wpos, full = d.full;
+        LZ_BCAST32(wpos);
+        LZ_BCAST32(full);
+        d.wpos = wpos;
+        d.full = full;
+
+        consumed = (uint64_t)(payload - io.in) + (short_payload ? in_rem : (uint64_t)csz);
+        if (st == LZGPU_OK || st == LZGPU_OK_INPUT_EXHAUSTED) {
+            if (!complete) {
+                // The coder wanted more input than the chunk holds.  At the end of a truncated
+                // stream the reference reports io.ErrUnexpectedEOF at the next header read;
+                // otherwise it would carry on with a short chunk (Q1/Q8): documented deviation.
+                if (short_payload) { status = LZGPU_UNEXPECTED_EOF; consumed = io.in_len; }
+                else { status = LZGPU_RESULT_ERROR; site = LZGPU_SITE_LZMA2_CHUNK_SIZE; }
+                break;
+            }
+            if (st == LZGPU_OK && !exact) {
+                // Decoded size reached with compressed bytes left over: the reference parses the
+                // next header from the middle of the payload (Q8).  Documented deviation.
+                status = LZGPU_RESULT_ERROR; site = LZGPU_SITE_LZMA2_CHUNK_SIZE;
+                break;
+            }
+            if (short_payload) { status = LZGPU_UNEXPECTED_EOF; consumed = io.in_len; break; }
+            ip = payload + csz;
+            continue;
+        }
+        status = (int32_t)st;
+        site = (int32_t)st_site;
+        break;
+    }
+
+    uint32_t code = d.code;
+    uint64_t outbits = (uint64_t)(uintptr_t)d.outp;
+    LZ_BCAST32(code);
+    LZ_BCAST64(outbits);
+    LZ_IF_LANE0 {
+        res.status = status;
+        res.err_site = site;
+        res.bytes_out = (uint64_t)((uint8_t *)(uintptr_t)outbits - io.out);
+        res.bytes_in = consumed;
+        res.final_code = code;
+    }
+}
+
+}  // namespace lzgpu

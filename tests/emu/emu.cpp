@@ -1,0 +1,46 @@
+// tests/emu/emu.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the *same* unit-decode code the CUDA kernel runs
+// (lzma_b200/csrc/lzgpu_unit.cuh + lzgpu_core.cuh) for the host, with the 32 lanes
+// of a warp emulated by loops and the deferred window stores reproduced exactly
+// (a value is captured when the kernel would issue the load and written when the
+// kernel would issue the store).  It lets the CPU-only test tier check the
+// decoder's logic and the copy protocol against the oracle.  It is never linked
+// into liblzgpu.so and is not a fallback: the product fails without a GPU.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../lzma_b200/csrc/lzgpu_prep.h"
+#include "../../lzma_b200/csrc/lzgpu_unit.cuh"
+
+using namespace lzgpu;
+
+extern "C" int emu_decode_batch(const lzgpu_unit *units, int64_t n, const uint8_t *in_base, uint64_t in_size,
+                                uint8_t *out_base, uint64_t out_size, lzgpu_result *results) {
+    for (int64_t i = 0; i < n; i++) {
+        lzgpu_unit u = units[i];
+        if (u.in_off > in_size || u.in_len > in_size - u.in_off || u.out_off > out_size || u.out_cap > out_size - u.out_off)
+            return LZGPU_E_INVALID;
+        lzgpu_result r;
+        bool alone = false;
+        if (!prepare_unit(u, r, &alone)) { results[i] = r; continue; }
+        const uint32_t bits = u.lit_bits;
+        std::vector<uint16_t> probs((size_t)P_FIXED + ((size_t)0x300 << bits) + 64, 0xDEAD);
+        UnitIO io;
+        io.in = in_base + u.in_off;
+        io.in_len = u.in_len;
+        io.out = out_base + u.out_off;
+        io.out_cap = u.out_cap;
+        memset(&r, 0, sizeof r);
+        r.status = LZGPU_NOT_RUN;
+        if (u.kind == LZGPU_KIND_LZMA2_GROUP) run_unit_lzma2(u, io, probs.data(), probs.data() + P_LIT, bits, r);
+        else run_unit_lzma1(u, io, probs.data(), probs.data() + P_LIT, r);
+        if (alone) r.bytes_in += 13;
+        r.device = -1;
+        results[i] = r;
+    }
+    return LZGPU_E_OK;
+}

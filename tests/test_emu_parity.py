@@ -1,0 +1,30 @@
+"""CPU tier: the kernel's unit-decode code (lzgpu_unit.cuh / lzgpu_core.cuh) compiled for the host
+with the warp's lanes emulated, against the oracle.  Checks decoder logic and the deferred-store
+copy protocol without a GPU; the GPU tier (test_gpu_parity.py) repeats it through liblzgpu.so."""
+import numpy as np
+import pytest
+
+import cases
+from backends import make_context
+from check import same_outcome
+from lzma_b200 import _lib as L
+from lzma_b200 import batch as B
+from oracle import oracle as O
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return make_context("emu")
+
+
+def test_alone_cases(ctx):
+    cs = cases.alone_cases(heavy=False)
+    got = B.decode_alone_streams(ctx, [c[1] for c in cs], [c[2] for c in cs])
+    for (name, s, cap), g in zip(cs, got):
+        same_outcome(O.lzma_alone(s, cap), g.status, g.err_site, g.data, name)
+
+
+def test_lzma2_cases(ctx):
+    for name, s, dict_size, cap in cases.lzma2_cases():
+        st, site, data = B.decode_lzma2_stream(ctx, s, dict_size)
+        same_outcome(O.lzma2(s, dict_size, cap + (1 << 20)), st, site, data, name, strict_site=False)

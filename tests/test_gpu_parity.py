@@ -1,0 +1,111 @@
+"""GPU tier: liblzgpu.so through the C ABI vs the oracle, on a real B200."""
+import ctypes as C
+import hashlib
+import zlib
+
+import numpy as np
+import pytest
+
+import cases
+from check import same_outcome
+from lzma_b200 import _lib as L
+from lzma_b200 import batch as B
+from lzma_b200 import corpus as K
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = B.Context([0])
+    yield c
+    c.close()
+
+
+def test_reference_assets(ctx):
+    """The reference's own test table (reader1_test.go:15-107, reader2_test.go:12-29)."""
+    names = cases.ALONE_ASSETS
+    got = B.decode_alone_streams(ctx, [cases.asset(n) for n in names])
+    for n, g in zip(names, got):
+        same_outcome(O.lzma_alone(cases.asset(n), 2 << 20), g.status, g.err_site, g.data, n)
+    by = dict(zip(names, got))
+    for n in ("a.lzma", "a_eos.lzma", "a_eos_and_size.lzma", "a_lp1_lc2_pb1.lzma"):
+        assert hashlib.md5(by[n].data).hexdigest() == "57a42eb7f425c13fa644f2618a097ab7"
+    assert hashlib.md5(by["randomfile.dat.lzma"].data).hexdigest() == "b2d18c4275c394a729607ff9fe0caae7"
+    assert (by["bad_corrupted.lzma"].status, by["bad_corrupted.lzma"].err_site) == (L.RESULT_ERROR, 652)
+    assert (by["bad_eos_incorrect_size.lzma"].status, by["bad_eos_incorrect_size.lzma"].err_site) == (L.RESULT_ERROR, 636)
+    assert (by["bad_incorrect_size.lzma"].status, by["bad_incorrect_size.lzma"].err_site) == (L.RESULT_ERROR, 46)
+    st, site, data = B.decode_lzma2_stream(ctx, cases.asset("randomfile.dat.lzma2"), 0)
+    assert st == L.OK and hashlib.md5(data).hexdigest() == "b2d18c4275c394a729607ff9fe0caae7"
+
+
+def test_alone_cases(ctx):
+    """Mixed batch: every lc/lp/pb liblzma can write, EOS-only / EOS+size / size-only streams, dictionary
+    wrap, runs, truncations, bit flips, bad headers -- one batch, one bad unit must not poison the rest."""
+    cs = cases.alone_cases(heavy=True)
+    got = B.decode_alone_streams(ctx, [c[1] for c in cs], [c[2] for c in cs])
+    for (name, s, cap), g in zip(cs, got):
+        same_outcome(O.lzma_alone(s, cap), g.status, g.err_site, g.data, name)
+
+
+def test_lzma2_cases(ctx):
+    for name, s, dict_size, cap in cases.lzma2_cases():
+        st, site, data = B.decode_lzma2_stream(ctx, s, dict_size)
+        same_outcome(O.lzma2(s, dict_size, cap + (1 << 20)), st, site, data, name, strict_site=False)
+
+
+def test_unknown_size_retry(ctx):
+    d = K.text_block(123, 3_000_000)     # ratio > the first capacity guess
+    g = B.decode_alone_streams(ctx, [K.compress_alone(d, preset=1)])[0]
+    assert g.status == L.OK and g.data == d
+
+
+def test_device_resident_plan(ctx):
+    """plan_create / plan_launch / plan_results with buffers already in HBM (what bench.py times)."""
+    import torch
+    plains = [K.text_block(i, 100_000 + 1000 * i) for i in range(40)]
+    streams = [K.compress_alone(p) for p in plains]
+    units, in_buf, out_size, _ = B.build_alone_batch(streams, [len(p) for p in plains])
+    d_in = torch.from_numpy(in_buf).cuda()
+    d_out = torch.zeros(out_size, dtype=torch.uint8, device="cuda")
+    plan = ctx.plan(units, in_buf.nbytes, out_size)
+    assert plan.launch_count == 1
+    for _ in range(2):
+        plan.launch(d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    res, st = plan.results()
+    out = d_out.cpu().numpy()
+    for k, p in enumerate(plains):
+        assert res[k].status == L.OK and res[k].bytes_out == len(p)
+        assert out[units[k].out_off:units[k].out_off + len(p)].tobytes() == p
+    assert st.kernel_ms > 0
+    plan.close()
+
+
+def test_full_size_batch_properties(ctx):
+    """BASELINE-sized units (1 MiB) in a batch larger than the SM count: checksum per unit against the
+    plaintext's, and the decoded size; every unit of the same stream must give the same bytes."""
+    distinct = 12
+    plains = [K.text_block(1000 + i, 1 << 20) for i in range(distinct)]
+    streams = [K.compress_alone(p) for p in plains]
+    n = 300
+    pick = [i % distinct for i in range(n)]
+    got = B.decode_alone_streams(ctx, [streams[i] for i in pick], [1 << 20] * n)
+    crcs = [zlib.crc32(p) for p in plains]
+    for i, g in zip(pick, got):
+        assert g.status == L.OK and len(g.data) == 1 << 20 and zlib.crc32(g.data) == crcs[i]
+
+
+def test_large_literal_tables_in_hbm(ctx):
+    """lc+lp > 4 needs literal tables beyond shared memory (the reference accepts any prop < 225,
+    reader1.go:210-221).  liblzma cannot write such streams, so build one by re-labelling: a stream
+    coded with lc=4,lp=0 read as lc=4 via a RAW unit whose declared lp is larger is NOT equivalent,
+    hence the check here is oracle == GPU on the same bytes, whatever they decode to."""
+    d = K.text_block(5, 60_000)
+    s = K.compress_alone(d, 4, 0, 2, 1 << 16)
+    for prop in (4 + 9 * (4 + 5 * 2), 8 + 9 * (0 + 5 * 0), 8 + 9 * (4 + 5 * 4)):   # lc4 lp4, lc8 lp0, lc8 lp4
+        t = bytes([prop]) + s[1:]
+        want = O.lzma_alone(t, 200_000)
+        g = B.decode_alone_streams(ctx, [t], [200_000])[0]
+        same_outcome(want, g.status, g.err_site, g.data, f"prop{prop}")
