@@ -252,7 +252,9 @@ def main():
     d_in = h_in.cuda(non_blocking=False)
     d_out = torch.empty(out_size, dtype=torch.uint8, device="cuda")
     plan = ctx.plan(units, in_size, out_size)
-    stream = torch.cuda.current_stream().cuda_stream
+    # torch's default stream has handle 0, which the C ABI reads as "use the context's own stream";
+    # cudaStreamLegacy (0x1) names the same stream explicitly, so torch's events bracket the kernels.
+    stream = torch.cuda.current_stream().cuda_stream or 1
 
     def step():
         plan.launch(d_in.data_ptr(), d_out.data_ptr(), stream)

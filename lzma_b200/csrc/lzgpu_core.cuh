@@ -35,6 +35,7 @@
 #define LZ_LD_IN32(p) __ldg(reinterpret_cast<const unsigned int *>(p))
 #define LZ_BSWAP32(x) __byte_perm((x), 0u, 0x0123u)
 #define LZ_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#define LZ_FUNNEL_L(lo, hi, sh) __funnelshift_l((lo), (hi), (sh))   /* ((hi:lo) << sh) >> 32, sh < 32 */
 #define LZ_LIKELY(x) __builtin_expect(!!(x), 1)
 #define LZ_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #else
@@ -42,6 +43,7 @@
 #define LZ_LD_IN32(p) (*(const uint32_t *)(p))
 #define LZ_BSWAP32(x) __builtin_bswap32(x)
 #define LZ_PREFETCH_L2(p) ((void)0)
+#define LZ_FUNNEL_L(lo, hi, sh) ((uint32_t)(((((uint64_t)(hi)) << 32 | (uint64_t)(lo)) << (sh)) >> 32))
 #define LZ_LIKELY(x) __builtin_expect(!!(x), 1)
 #define LZ_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #endif
@@ -73,8 +75,10 @@ enum : uint32_t { OP_COPY = 0, OP_COPY_Q4 = 1, OP_DONE = 2 };
 // Lane 0's decoder registers.
 struct Dec {
     uint32_t range, code;
-    uint32_t inbuf, incnt;          // next input bytes, most significant first
-    const uint8_t *ip, *in_end;
+    uint32_t inb_hi, inb_lo;        // 64-bit input lookahead, next byte in the top 8 bits of inb_hi
+    uint32_t inbits;                // bits in the lookahead (real bytes first, then phantom zeros)
+    uint32_t phantom;               // zero BITS appended after the real input ran out
+    const uint8_t *ip, *in_end;     // next byte to load / end of the real input
     uint32_t rep0, rep1, rep2, rep3, state;
     uint32_t wpos, dict_size;       // window.pos (wrapped, Q3) and window.size
     uint32_t full;                  // window.isFull
@@ -86,25 +90,50 @@ struct Dec {
     int32_t status, site;
 };
 
-LZ_HD bool rc_refill(Dec &d) {
+// Input is consumed through a 64-bit lookahead register so that the per-bit
+// normalisation is branch-free; LZ_FILL() tops it up to >= 4 bytes and is placed so
+// that at most 4 bit steps run between two fills.  When the real input runs out the
+// lookahead is padded with zero bytes that are counted in d.phantom: the reference
+// stops (io.EOF from ReadByte, decompress.go:35-38) exactly when the decoder would
+// consume the first of them, i.e. when d.phantom > d.inbits, which is tested before
+// anything a symbol decides becomes visible.
+LZ_HD void rc_put(Dec &d, uint32_t w, uint32_t nbits) {   // append the top nbits of w (inbits <= 32)
+    // lookahead = hi:lo, valid bits at the top; new bits go right below them
+    const uint32_t k = d.inbits;
+    if (k == 32) { d.inb_lo |= w; }
+    else if (k == 0) { d.inb_hi |= w; }
+    else { d.inb_hi |= w >> k; d.inb_lo |= w << (32 - k); }
+    d.inbits = k + nbits;
+}
+LZ_HD void rc_fill(Dec &d) {
     const uint64_t rem = (uint64_t)(d.in_end - d.ip);
-    if (rem == 0) return false;
-    const uint32_t mis = (uint32_t)((uintptr_t)d.ip & 3u);
-    if (LZ_LIKELY(mis == 0 && rem >= 4)) {
-        d.inbuf = LZ_BSWAP32(LZ_LD_IN32(d.ip));
-        d.incnt = 4;
-        d.ip += 4;
+    if (LZ_LIKELY(rem >= 4 && ((uintptr_t)d.ip & 3u) == 0)) {
+        const uint32_t w = LZ_BSWAP32(LZ_LD_IN32(d.ip));
         if (((uintptr_t)d.ip & 127u) == 0) LZ_PREFETCH_L2(d.ip + 256);
-    } else {
-        uint32_t n = 4 - mis;
-        if (n > rem) n = (uint32_t)rem;
-        uint32_t w = 0;
-        for (uint32_t i = 0; i < n; i++) w |= (uint32_t)LZ_LD_IN8(d.ip + i) << (24 - 8 * i);
-        d.inbuf = w;
-        d.incnt = n;
-        d.ip += n;
+        d.ip += 4;
+        rc_put(d, w, 32);
+        return;
     }
-    return true;
+    // unaligned start or the last few bytes: byte by byte up to a word boundary
+    while (d.ip < d.in_end && (d.inbits < 32 || (((uintptr_t)d.ip & 3u) != 0 && d.inbits < 64))) {
+        const uint32_t b = LZ_LD_IN8(d.ip);
+        if (d.inbits < 32) d.inb_hi |= b << (24 - d.inbits);
+        else d.inb_lo |= b << (56 - d.inbits);
+        d.ip++;
+        d.inbits += 8;
+    }
+    if (d.inbits < 32) {   // real input exhausted: pad with phantom zeros
+        d.phantom += 32 - d.inbits;
+        d.inbits = 32;
+    }
+}
+#define LZ_FILL() do { if (LZ_UNLIKELY(d.inbits < 32)) rc_fill(d); } while (0)
+#define LZ_EXHAUSTED() (d.phantom > d.inbits)
+
+// real input bytes consumed so far, given the start of the input
+LZ_HD uint64_t rc_consumed(const Dec &d, const uint8_t *start) {
+    const uint32_t unread = d.inbits > d.phantom ? (d.inbits - d.phantom) >> 3 : 0;
+    return (uint64_t)(d.ip - start) - unread;
 }
 
 // Range-coder preamble: rangeDecoder.Init, range_decoder.go:27-46.
@@ -112,8 +141,9 @@ LZ_HD bool rc_refill(Dec &d) {
 LZ_HD int rc_init(Dec &d) {
     d.range = 0xFFFFFFFFu;
     d.code = 0;
-    d.inbuf = 0;
-    d.incnt = 0;
+    d.inb_hi = d.inb_lo = 0;
+    d.inbits = 0;
+    d.phantom = 0;
     if ((uint64_t)(d.in_end - d.ip) < 1) return -1;
     if (LZ_LD_IN8(d.ip) != 0) return 1;
     if ((uint64_t)(d.in_end - d.ip) < 5) { d.ip = d.in_end; return -1; }
@@ -124,87 +154,106 @@ LZ_HD int rc_init(Dec &d) {
     return 0;
 }
 
-// One adaptive bit (DecodeBit, range_decoder.go:57-98) with the reference's
-// normalise-after-the-bit order.  On input exhaustion jumps to input_eof.
-#define LZ_NORM()                                                         \
-    do {                                                                  \
-        if (d.range < kTop) {                                             \
-            if (LZ_UNLIKELY(d.incnt == 0)) {                              \
-                if (!rc_refill(d)) goto input_eof;                        \
-            }                                                             \
-            d.range <<= 8;                                                \
-            d.code = (d.code << 8) | (d.inbuf >> 24);                     \
-            d.inbuf <<= 8;                                                \
-            d.incnt--;                                                    \
-        }                                                                 \
+// Normalise AFTER the bit, as the reference does (range_decoder.go:64-75).  Select form:
+// no branch, so no convergence barrier and no fetch bubble in lane 0's instruction stream.
+#define LZ_NORM()                                                                   \
+    do {                                                                            \
+        const uint32_t sh_ = d.range < kTop ? 8u : 0u;                              \
+        d.range <<= sh_;                                                            \
+        d.code = LZ_FUNNEL_L(d.inb_hi, d.code, sh_);                                \
+        d.inb_hi = LZ_FUNNEL_L(d.inb_lo, d.inb_hi, sh_);                            \
+        d.inb_lo <<= sh_;                                                           \
+        d.inbits -= sh_;                                                            \
     } while (0)
 
-#define LZ_BIT(PP, BIT)                                                   \
-    do {                                                                  \
-        uint16_t *pp_ = (PP);                                             \
-        const uint32_t p_ = *pp_;                                         \
-        const uint32_t bound_ = (d.range >> 11) * p_;                     \
-        if (d.code < bound_) {                                            \
-            d.range = bound_;                                             \
-            *pp_ = (uint16_t)(p_ + ((2048u - p_) >> 5));                  \
-            (BIT) = 0;                                                    \
-        } else {                                                          \
-            d.range -= bound_;                                            \
-            d.code -= bound_;                                             \
-            *pp_ = (uint16_t)(p_ - (p_ >> 5));                            \
-            (BIT) = 1;                                                    \
-        }                                                                 \
-        LZ_NORM();                                                        \
+// One adaptive bit (DecodeBit, range_decoder.go:57-98), select form.
+// Probability update: p + ((2048 - p) >> 5) for a 0, p - (p >> 5) for a 1; the latter equals
+// p + ((31 - p) >> 5) with an arithmetic shift, so both are p + ((k - p) >> 5).
+#define LZ_BIT(PP, BIT)                                                             \
+    do {                                                                            \
+        uint16_t *pp_ = (PP);                                                       \
+        const uint32_t p_ = *pp_;                                                   \
+        const uint32_t bound_ = (d.range >> 11) * p_;                               \
+        const bool one_ = d.code >= bound_;                                         \
+        d.range = one_ ? d.range - bound_ : bound_;                                 \
+        d.code = one_ ? d.code - bound_ : d.code;                                   \
+        *pp_ = (uint16_t)(p_ + (uint32_t)((int32_t)((one_ ? 31u : 2048u) - p_) >> 5)); \
+        (BIT) = one_ ? 1u : 0u;                                                     \
+        LZ_NORM();                                                                  \
     } while (0)
 
-// MSB-first bit tree (BitTreeDecode, bit_tree_decoder.go:26-76)
-#define LZ_TREE(PROBS, NBITS, OUT)                                        \
-    do {                                                                  \
-        uint16_t *tp_ = (PROBS);                                          \
-        uint32_t m_ = 1, b_;                                              \
-        for (int i_ = 0; i_ < (NBITS); i_++) {                            \
-            LZ_BIT(tp_ + m_, b_);                                         \
-            m_ = (m_ << 1) | b_;                                          \
-        }                                                                 \
-        (OUT) = m_ - (1u << (NBITS));                                     \
+// One equiprobable bit (DecodeDirectBits, range_decoder.go:100-134 / decompress.go:549-576)
+#define LZ_DIRECT(RES)                                                              \
+    do {                                                                            \
+        d.range >>= 1;                                                              \
+        const bool one_ = d.code >= d.range;                                        \
+        d.code = one_ ? d.code - d.range : d.code;                                  \
+        (RES) = ((RES) << 1) | (one_ ? 1u : 0u);                                    \
+        LZ_NORM();                                                                  \
     } while (0)
 
-// LSB-first bit tree (BitTreeReverseDecode, bit_tree_decoder.go:82-135)
-#define LZ_TREE_REV(PROBS, NBITS, OUT)                                    \
-    do {                                                                  \
-        uint16_t *tp_ = (PROBS);                                          \
-        uint32_t m_ = 1, b_, s_ = 0;                                      \
-        for (uint32_t i_ = 0; i_ < (uint32_t)(NBITS); i_++) {             \
-            LZ_BIT(tp_ + m_, b_);                                         \
-            m_ = (m_ << 1) | b_;                                          \
-            s_ |= b_ << i_;                                               \
-        }                                                                 \
-        (OUT) = s_;                                                       \
+// MSB-first bit tree (BitTreeDecode, bit_tree_decoder.go:26-76), NBITS constant, unrolled.
+// FILL_AT: a fill is issued before bit i whenever (i & 3) == FILL_AT (keeps <= 4 steps per fill).
+#define LZ_TREE(PROBS, NBITS, OUT, FILL_AT)                                         \
+    do {                                                                            \
+        uint16_t *tp_ = (PROBS);                                                    \
+        uint32_t m_ = 1, b_;                                                        \
+        _Pragma("unroll") for (int i_ = 0; i_ < (NBITS); i_++) {                    \
+            if ((i_ & 3) == (FILL_AT)) LZ_FILL();                                   \
+            LZ_BIT(tp_ + m_, b_);                                                   \
+            m_ = (m_ << 1) | b_;                                                    \
+        }                                                                           \
+        (OUT) = m_ - (1u << (NBITS));                                               \
     } while (0)
 
-// lenDecoder.Decode (len_decoder.go:34-60); WHICH = 0 low, 1 mid, 2 high
-#define LZ_LEN(LP, POS_STATE, LEN, WHICH)                                 \
-    do {                                                                  \
-        uint16_t *lp_ = (LP);                                             \
-        uint32_t lb_, lv_;                                                \
-        LZ_BIT(lp_ + LEN_CHOICE, lb_);                                    \
-        if (lb_ == 0) {                                                   \
-            LZ_TREE(lp_ + LEN_LOW + ((POS_STATE) << 3), 3, lv_);          \
-            (LEN) = lv_; (WHICH) = 0;                                     \
-        } else {                                                          \
-            LZ_BIT(lp_ + LEN_CHOICE2, lb_);                               \
-            if (lb_ == 0) {                                               \
-                LZ_TREE(lp_ + LEN_MID + ((POS_STATE) << 3), 3, lv_);      \
-                (LEN) = 8 + lv_; (WHICH) = 1;                             \
-            } else {                                                      \
-                LZ_TREE(lp_ + LEN_HIGH, 8, lv_);                          \
-                (LEN) = 16 + lv_; (WHICH) = 2;                            \
-            }                                                             \
-        }                                                                 \
+// LSB-first bit tree (BitTreeReverseDecode, bit_tree_decoder.go:82-135), runtime NBITS <= 5
+#define LZ_TREE_REV(PROBS, NBITS, OUT, MAXBITS)                                     \
+    do {                                                                            \
+        uint16_t *tp_ = (PROBS);                                                    \
+        uint32_t m_ = 1, b_, s_ = 0;                                                \
+        const uint32_t nb_ = (NBITS);                                               \
+        _Pragma("unroll") for (uint32_t i_ = 0; i_ < (MAXBITS); i_++) {             \
+            if (i_ < nb_) {                                                         \
+                if (i_ == 4) LZ_FILL();                                             \
+                LZ_BIT(tp_ + m_, b_);                                               \
+                m_ = (m_ << 1) | b_;                                                \
+                s_ |= b_ << i_;                                                     \
+            }                                                                       \
+        }                                                                           \
+        (OUT) = s_;                                                                 \
     } while (0)
 
+// lenDecoder.Decode (len_decoder.go:34-60); WHICH = 0 low, 1 mid, 2 high.
+// Entered with >= 2 lookahead bytes to spare; leaves by itself filled as needed.
+#define LZ_LEN(LP, POS_STATE, LEN, WHICH)                                           \
+    do {                                                                            \
+        uint16_t *lp_ = (LP);                                                       \
+        uint32_t lb_, lv_;                                                          \
+        LZ_BIT(lp_ + LEN_CHOICE, lb_);                                              \
+        if (lb_ == 0) {                                                             \
+            LZ_FILL();                                                              \
+            LZ_TREE(lp_ + LEN_LOW + ((POS_STATE) << 3), 3, lv_, 7);                 \
+            (LEN) = lv_; (WHICH) = 0;                                               \
+        } else {                                                                    \
+            LZ_BIT(lp_ + LEN_CHOICE2, lb_);                                         \
+            LZ_FILL();                                                              \
+            if (lb_ == 0) {                                                         \
+                LZ_TREE(lp_ + LEN_MID + ((POS_STATE) << 3), 3, lv_, 7);             \
+                (LEN) = 8 + lv_; (WHICH) = 1;                                       \
+            } else {                                                                \
+                LZ_TREE(lp_ + LEN_HIGH, 8, lv_, 0);                                 \
+                (LEN) = 16 + lv_; (WHICH) = 2;                                      \
+            }                                                                       \
+        }                                                                           \
+    } while (0)
+
+// An error return.  The reference would have returned io.EOF from the failing ReadByte
+// before reaching any later check, so input exhaustion is tested first.
 #define LZ_FAIL(ST, SITE)                                                 \
-    do { d.status = (ST); d.site = (SITE); return OP_DONE; } while (0)
+    do {                                                                  \
+        if (LZ_EXHAUSTED()) goto input_eof;                               \
+        d.status = (ST); d.site = (SITE); return OP_DONE;                 \
+    } while (0)
 
 // Runs lane 0's serial decoder until a symbol needs the warp (a match / rep /
 // short rep: OP_COPY or OP_COPY_Q4 with len and dist set, window position already
@@ -216,36 +265,41 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
         // decompress.go:14-20
         if (at_end && d.end_is_size && d.code == 0) LZ_FAIL(LZGPU_OK, 0);
 
+        LZ_FILL();
         const uint32_t pos_state = d.wpos & d.pos_mask;          // :22
         const uint32_t state2 = (d.state << 4) + pos_state;      // :23
         uint32_t bit;
         LZ_BIT(P + P_IS_MATCH + state2, bit);                    // :25-42
 
         if (bit == 0) {  // literal, :44-175
-            if (at_end) {
+            if (LZ_UNLIKELY(at_end)) {
                 if (d.end_is_size) LZ_FAIL(LZGPU_RESULT_ERROR, 46);
                 LZ_FAIL(LZGPU_OUTPUT_OVERFLOW, 0);
             }
             uint16_t *pr = L + 0x300u * (((d.wpos & d.lp_mask) << d.lc) + (d.prev_byte >> (8 - d.lc)));  // :56-57
+            // Plain and matched literals in one straight-line tree walk: `offs` is 0x100 while
+            // the decoded prefix still equals the match byte's (matched mode, state >= 7,
+            // :59-114) and drops to 0 at the first mismatch, after which the index is the
+            // plain one (:127-166).  Index = offs + match_bit + sym = ((1 + matchBit) << 8) + sym.
+            uint32_t offs = d.state >= 7 ? 0x100u : 0u;
+            uint32_t mb = d.mbyte;
             uint32_t sym = 1;
-            if (d.state >= 7) {  // matched literal, :59-114
-                uint32_t mb = d.mbyte;
-                do {
-                    const uint32_t mbit = (mb >> 7) & 1;
-                    mb <<= 1;
-                    LZ_BIT(pr + ((1 + mbit) << 8) + sym, bit);
-                    sym = (sym << 1) | bit;
-                    if (mbit != bit) break;
-                } while (sym < 0x100);
-            }
-            while (sym < 0x100) {  // :127-166
-                LZ_BIT(pr + sym, bit);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if ((i & 3) == 3) LZ_FILL();
+                mb += mb;
+                const uint32_t old = offs;
+                offs &= mb;                                      // match bit, if still in matched mode
+                LZ_BIT(pr + offs + old + sym, bit);
                 sym = (sym << 1) | bit;
+                offs ^= bit ? 0u : old;                          // stays set only while bit == match bit
             }
+            if (LZ_UNLIKELY(LZ_EXHAUSTED())) goto input_eof;
             sym &= 0xFF;
             *d.outp++ = (uint8_t)sym;                             // PutByte, :168
             d.prev_byte = sym;
-            if (++d.wpos >= d.dict_size) { d.wpos -= d.dict_size; d.full = 1; }
+            d.wpos++;
+            if (LZ_UNLIKELY(d.wpos >= d.dict_size)) { d.wpos -= d.dict_size; d.full = 1; }
             d.state = d.state < 4 ? 0 : (d.state < 10 ? d.state - 3 : d.state - 6);  // stateUpdateLiteral
             continue;
         }
@@ -259,32 +313,30 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
             d.state = d.state < 7 ? 7 : 10;                       // stateUpdateMatch, :431
             const uint32_t len_state = len > 3 ? 3 : len;         // :434-437
             uint32_t slot;
-            LZ_TREE(P + P_POS_SLOT + (len_state << 6), 6, slot);  // :441-486
+            LZ_TREE(P + P_POS_SLOT + (len_state << 6), 6, slot, 0);  // :441-486
             if (slot < 4) {
                 d.rep0 = slot;                                    // :488-489
             } else {
                 const uint32_t nd = (slot >> 1) - 1;
                 uint32_t dist = (2 | (slot & 1)) << nd, v;
+                LZ_FILL();
                 if (slot < 14) {                                  // :494-546
-                    LZ_TREE_REV(P + P_POS_DEC + dist - slot, nd, v);
+                    LZ_TREE_REV(P + P_POS_DEC + dist - slot, nd, v, 5);
                     dist += v;
                 } else {                                          // :548-628
                     uint32_t res = 0;
                     for (uint32_t n = nd - 4; n > 0; n--) {       // DecodeDirectBits, :549-576
-                        d.range >>= 1;
-                        d.code -= d.range;
-                        const uint32_t t = 0u - (d.code >> 31);
-                        d.code += d.range & t;
-                        res = (res << 1) + (t + 1);
-                        LZ_NORM();
+                        if ((n & 3) == 0) LZ_FILL();
+                        LZ_DIRECT(res);
                     }
                     dist += res << 4;
-                    LZ_TREE_REV(P + P_ALIGN, 4, v);               // :580-625
+                    LZ_FILL();
+                    LZ_TREE_REV(P + P_ALIGN, 4, v, 4);            // :580-625
                     dist += v;
                 }
                 d.rep0 = dist;
             }
-            if (d.rep0 == 0xFFFFFFFFu) {                          // EOS marker, :633-645
+            if (LZ_UNLIKELY(d.rep0 == 0xFFFFFFFFu)) {             // EOS marker, :633-645
                 if (d.code == 0) {
                     // sizeDefined && bytesLeft > 0 (a cap below the declared size implies bytes left)
                     if (d.size_defined && !(d.end_is_size && at_end)) LZ_FAIL(LZGPU_RESULT_ERROR, 636);
@@ -292,20 +344,20 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
                 }
                 LZ_FAIL(LZGPU_RESULT_ERROR, 643);
             }
-            if (at_end) {                                         // :647-649
+            if (LZ_UNLIKELY(at_end)) {                            // :647-649
                 if (d.end_is_size) LZ_FAIL(LZGPU_RESULT_ERROR, 648);
                 LZ_FAIL(LZGPU_OUTPUT_OVERFLOW, 0);
             }
-            if (d.rep0 >= d.dict_size || !(d.full || d.rep0 <= d.wpos))  // :651-653 (Q4 as written)
+            if (LZ_UNLIKELY(d.rep0 >= d.dict_size || !(d.full || d.rep0 <= d.wpos)))  // :651-653 (Q4 as written)
                 LZ_FAIL(LZGPU_RESULT_ERROR, 652);
             len += 2;                                             // :656
             trunc_site = 662;
         } else {  // rep match, :685-1118
-            if (at_end) {                                         // :686-688
+            if (LZ_UNLIKELY(at_end)) {                            // :686-688
                 if (d.end_is_size) LZ_FAIL(LZGPU_RESULT_ERROR, 687);
                 LZ_FAIL(LZGPU_OUTPUT_OVERFLOW, 0);
             }
-            if (d.wpos == 0 && !d.full) LZ_FAIL(LZGPU_RESULT_ERROR, 691);  // IsEmpty, :690-692
+            if (LZ_UNLIKELY(d.wpos == 0 && !d.full)) LZ_FAIL(LZGPU_RESULT_ERROR, 691);  // IsEmpty, :690-692
             bool short_rep = false;
             LZ_BIT(rep4 + 1, bit);                                // isRepG0, :694-772
             if (bit == 0) {
@@ -317,6 +369,7 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
                 if (bit == 0) {
                     dist = d.rep1; d.rep1 = d.rep0; d.rep0 = dist;
                 } else {
+                    LZ_FILL();
                     LZ_BIT(rep4 + 3, bit);                        // isRepG2, :816-861
                     if (bit == 0) { dist = d.rep2; d.rep2 = d.rep1; d.rep1 = d.rep0; d.rep0 = dist; }
                     else { dist = d.rep3; d.rep3 = d.rep2; d.rep2 = d.rep1; d.rep1 = d.rep0; d.rep0 = dist; }
@@ -327,18 +380,20 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
                 len = 1;
                 trunc_site = 0;
             } else {
+                LZ_FILL();
                 LZ_LEN(P + P_LEN1, pos_state, len, which);        // :870-1101
                 d.state = d.state < 7 ? 8 : 11;                   // stateUpdateRep
                 len += 2;
                 trunc_site = which == 0 ? 941 : (which == 1 ? 1035 : 1111);
             }
         }
+        if (LZ_UNLIKELY(LZ_EXHAUSTED())) goto input_eof;
 
         // copy: decompress.go:656-668 / :934-947 / :1028-1041 / :1104-1117
         const uint64_t avail = (uint64_t)(d.out_end - d.outp);
         if (d.end_is_size) {
-            if ((uint32_t)avail < len) LZ_FAIL(LZGPU_RESULT_ERROR, trunc_site);  // uint32(bytesLeft) < length (Q10)
-        } else if (avail < len) {
+            if (LZ_UNLIKELY((uint32_t)avail < len)) LZ_FAIL(LZGPU_RESULT_ERROR, trunc_site);  // uint32(bytesLeft) < length (Q10)
+        } else if (LZ_UNLIKELY(avail < len)) {
             LZ_FAIL(LZGPU_OUTPUT_OVERFLOW, 0);
         }
         const uint32_t dist = d.rep0 + 1;
@@ -352,7 +407,7 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
             op = OP_COPY_Q4;
         }
         d.wpos += len;
-        if (d.wpos >= d.dict_size) { d.wpos -= d.dict_size; d.full = 1; }
+        if (LZ_UNLIKELY(d.wpos >= d.dict_size)) { d.wpos -= d.dict_size; d.full = 1; }
         out_len = len;
         out_dist = dist;
         return op;

@@ -187,7 +187,7 @@ LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
         res.status = d.status;
         res.err_site = d.site;
         res.bytes_out = (uint64_t)(d.outp - io.out);
-        res.bytes_in = (uint64_t)(d.ip - io.in) - d.incnt;
+        res.bytes_in = rc_consumed(d, io.in);
         res.final_code = d.code;
     }
 }
@@ -209,8 +209,9 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     d.state = 0;
     d.range = 0xFFFFFFFFu;
     d.code = 0;
-    d.inbuf = 0;
-    d.incnt = 0;
+    d.inb_hi = d.inb_lo = 0;
+    d.inbits = 0;
+    d.phantom = 0;
     d.outp = io.out;
     d.out_end = io.out;
     d.end_is_size = 1;
@@ -347,7 +348,7 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
         uint64_t outbits = 0;
         LZ_IF_LANE0 {
             complete = d.outp == d.out_end && d.end_is_size;
-            exact = (d.ip - d.incnt) == d.in_end;
+            exact = rc_consumed(d, payload) == (uint64_t)(d.in_end - payload);
             outbits = (uint64_t)(uintptr_t)d.outp;
         }
         LZ_BCAST32(st);

@@ -72,7 +72,7 @@ def test_device_resident_plan(ctx):
     plan = ctx.plan(units, in_buf.nbytes, out_size)
     assert plan.launch_count == 1
     for _ in range(2):
-        plan.launch(d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        plan.launch(d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream or 1)
     torch.cuda.synchronize()
     res, st = plan.results()
     out = d_out.cpu().numpy()
