@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <numeric>
@@ -21,6 +22,10 @@
 #include "lzgpu_unit.cuh"
 
 using namespace lzgpu;
+
+#ifndef LZGPU_DEFAULT_VARIANT
+#define LZGPU_DEFAULT_VARIANT 2
+#endif
 
 // ------------------------------------------------------------------ kernel
 struct KArgs {
@@ -37,7 +42,7 @@ struct KArgs {
 
 // One warp per CTA, one unit per warp.  Fixed tables (3.7 KB) always in shared
 // memory; literal tables in shared memory when lc+lp <= 4 (<= 24 KB), else in HBM.
-template <bool kLitGlobal>
+template <bool kLitGlobal, int kV>
 __global__ void __launch_bounds__(32) lzgpu_decode_kernel(const KArgs a) {
     extern __shared__ __align__(16) uint16_t smem_probs[];
     const uint32_t slot = a.slot0 + blockIdx.x;
@@ -51,8 +56,26 @@ __global__ void __launch_bounds__(32) lzgpu_decode_kernel(const KArgs a) {
     io.out = a.out_base + u.out_off;
     io.out_cap = u.out_cap;
     lzgpu_result &res = a.results[ui];
-    if (u.kind == LZGPU_KIND_LZMA2_GROUP) run_unit_lzma2(u, io, P, L, a.lit_bits_cap, res);
-    else run_unit_lzma1(u, io, P, L, res);
+    if (u.kind == LZGPU_KIND_LZMA2_GROUP) run_unit_lzma2<kV>(u, io, P, L, a.lit_bits_cap, res);
+    else run_unit_lzma1<kV>(u, io, P, L, res);
+}
+
+// Tuning variant of the decoder (lzgpu_core.cuh, V_*): LZGPU_VARIANT in the environment
+// overrides the default; read once per plan.
+static int decoder_variant() {
+    const char *e = getenv("LZGPU_VARIANT");
+    if (e && *e >= '0' && *e <= '3') return *e - '0';
+    return LZGPU_DEFAULT_VARIANT;
+}
+
+template <bool kLitGlobal>
+static void launch_decode(int variant, unsigned grid, size_t smem, cudaStream_t st, const KArgs &a) {
+    switch (variant) {
+        case 1: lzgpu_decode_kernel<kLitGlobal, 1><<<grid, 32, smem, st>>>(a); break;
+        case 2: lzgpu_decode_kernel<kLitGlobal, 2><<<grid, 32, smem, st>>>(a); break;
+        case 3: lzgpu_decode_kernel<kLitGlobal, 3><<<grid, 32, smem, st>>>(a); break;
+        default: lzgpu_decode_kernel<kLitGlobal, 0><<<grid, 32, smem, st>>>(a); break;
+    }
 }
 
 // ------------------------------------------------------------------ errors
@@ -278,6 +301,7 @@ struct lzgpu_plan {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t last_stream = nullptr;
     bool launched = false;
+    int variant = 0;
 };
 
 extern "C" int lzgpu_ctx_create(const int *devices, int n_devices, lzgpu_ctx **out) {
@@ -339,6 +363,7 @@ extern "C" int lzgpu_plan_create(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit
     lzgpu_plan *p = new lzgpu_plan();
     p->ctx = ctx;
     p->dev_index = dev_index;
+    p->variant = decoder_variant();
     p->n = n;
     p->in_size = in_size;
     p->out_size = out_size;
@@ -444,8 +469,8 @@ extern "C" int lzgpu_plan_launch(lzgpu_plan *p, const uint8_t *d_in, uint8_t *d_
         a.lit_ws_stride = p->lit_ws_stride;
         a.lit_bits_cap = L.lit_bits;
         a.slot0 = L.slot0;
-        if (L.lit_global) lzgpu_decode_kernel<true><<<L.count, 32, L.smem, st>>>(a);
-        else lzgpu_decode_kernel<false><<<L.count, 32, L.smem, st>>>(a);
+        if (L.lit_global) launch_decode<true>(p->variant, L.count, L.smem, st, a);
+        else launch_decode<false>(p->variant, L.count, L.smem, st, a);
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaEventRecord(p->ev1, st));

@@ -36,6 +36,7 @@
 #define LZ_BSWAP32(x) __byte_perm((x), 0u, 0x0123u)
 #define LZ_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #define LZ_FUNNEL_L(lo, hi, sh) __funnelshift_l((lo), (hi), (sh))   /* ((hi:lo) << sh) >> 32, sh < 32 */
+#define LZ_CLZ(x) ((uint32_t)__clz((int)(x)))
 #define LZ_LIKELY(x) __builtin_expect(!!(x), 1)
 #define LZ_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #else
@@ -44,6 +45,7 @@
 #define LZ_BSWAP32(x) __builtin_bswap32(x)
 #define LZ_PREFETCH_L2(p) ((void)0)
 #define LZ_FUNNEL_L(lo, hi, sh) ((uint32_t)(((((uint64_t)(hi)) << 32 | (uint64_t)(lo)) << (sh)) >> 32))
+#define LZ_CLZ(x) ((uint32_t)__builtin_clz(x))
 #define LZ_LIKELY(x) __builtin_expect(!!(x), 1)
 #define LZ_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #endif
@@ -127,7 +129,23 @@ LZ_HD void rc_fill(Dec &d) {
         d.inbits = 32;
     }
 }
-#define LZ_FILL() do { if (LZ_UNLIKELY(d.inbits < 32)) rc_fill(d); } while (0)
+// Tuning variants (template parameter kV of decode_run; chosen per launch):
+//   V_NORM_BRANCH  normalise under a rarely-taken branch that also tops up the lookahead
+//                  (fewer instructions per bit, one convergence-barrier pair per bit);
+//                  otherwise normalise with selects and top up at LZ_FILL() points
+//   V_DIRECT_GROUP equiprobable bits in runs between two normalisations (their position is
+//                  known from the range's leading zeros) instead of a full step per bit
+enum : int { V_NORM_BRANCH = 1, V_DIRECT_GROUP = 2 };
+#define LZ_FILL32() do { if (LZ_UNLIKELY(d.inbits < 32)) rc_fill(d); } while (0)
+#define LZ_FILL() do { if (!(kV & V_NORM_BRANCH)) LZ_FILL32(); } while (0)
+#define LZ_SHIFT8()                                                                 \
+    do {                                                                            \
+        d.range <<= 8;                                                              \
+        d.code = (d.code << 8) | (d.inb_hi >> 24);                                  \
+        d.inb_hi = (d.inb_hi << 8) | (d.inb_lo >> 24);                              \
+        d.inb_lo <<= 8;                                                             \
+        d.inbits -= 8;                                                              \
+    } while (0)
 #define LZ_EXHAUSTED() (d.phantom > d.inbits)
 
 // real input bytes consumed so far, given the start of the input
@@ -158,12 +176,19 @@ LZ_HD int rc_init(Dec &d) {
 // no branch, so no convergence barrier and no fetch bubble in lane 0's instruction stream.
 #define LZ_NORM()                                                                   \
     do {                                                                            \
-        const uint32_t sh_ = d.range < kTop ? 8u : 0u;                              \
-        d.range <<= sh_;                                                            \
-        d.code = LZ_FUNNEL_L(d.inb_hi, d.code, sh_);                                \
-        d.inb_hi = LZ_FUNNEL_L(d.inb_lo, d.inb_hi, sh_);                            \
-        d.inb_lo <<= sh_;                                                           \
-        d.inbits -= sh_;                                                            \
+        if (kV & V_NORM_BRANCH) {                                                   \
+            if (LZ_UNLIKELY(d.range < kTop)) {                                      \
+                if (LZ_UNLIKELY(d.inbits < 8)) rc_fill(d);                          \
+                LZ_SHIFT8();                                                        \
+            }                                                                       \
+        } else {                                                                    \
+            const uint32_t sh_ = d.range < kTop ? 8u : 0u;                          \
+            d.range <<= sh_;                                                        \
+            d.code = LZ_FUNNEL_L(d.inb_hi, d.code, sh_);                            \
+            d.inb_hi = LZ_FUNNEL_L(d.inb_lo, d.inb_hi, sh_);                        \
+            d.inb_lo <<= sh_;                                                       \
+            d.inbits -= sh_;                                                        \
+        }                                                                           \
     } while (0)
 
 // One adaptive bit (DecodeBit, range_decoder.go:57-98), select form.
@@ -259,6 +284,7 @@ LZ_HD int rc_init(Dec &d) {
 // short rep: OP_COPY or OP_COPY_Q4 with len and dist set, window position already
 // advanced) or the unit part ends (OP_DONE with d.status / d.site set).
 // P: fixed tables (shared memory), L: literal tables (shared or global).
+template <int kV>
 LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, uint32_t &out_dist) {
     for (;;) {
         const bool at_end = (d.outp == d.out_end);
@@ -325,9 +351,31 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
                     dist += v;
                 } else {                                          // :548-628
                     uint32_t res = 0;
-                    for (uint32_t n = nd - 4; n > 0; n--) {       // DecodeDirectBits, :549-576
-                        if ((n & 3) == 0) LZ_FILL();
-                        LZ_DIRECT(res);
+                    if (kV & V_DIRECT_GROUP) {
+                        // DecodeDirectBits (:549-576) normalises when the halved range drops below
+                        // 2^24: first after g = 8 - clz(range) halvings, then after every 8th.
+                        // At most 4 normalisations for 26 bits: one top-up covers them.
+                        LZ_FILL32();
+                        uint32_t n = nd - 4;
+                        uint32_t g = 8 - LZ_CLZ(d.range);
+                        for (;;) {
+                            uint32_t k = n < g ? n : g;
+                            n -= k;
+                            g -= k;
+                            for (; k > 0; k--) {
+                                d.range >>= 1;
+                                const bool one = d.code >= d.range;
+                                d.code -= one ? d.range : 0u;
+                                res = (res << 1) | (one ? 1u : 0u);
+                            }
+                            if (g == 0) { LZ_SHIFT8(); g = 8; }
+                            if (n == 0) break;
+                        }
+                    } else {
+                        for (uint32_t n = nd - 4; n > 0; n--) {   // DecodeDirectBits, :549-576
+                            if ((n & 3) == 0) LZ_FILL();
+                            LZ_DIRECT(res);
+                        }
                     }
                     dist += res << 4;
                     LZ_FILL();
@@ -423,5 +471,7 @@ input_eof:
 // Byte i of a match comes from dst[src_index(i) - dist]; src_index(i) < dist always,
 // so every source byte predates the match: loads never depend on this match's stores.
 LZ_HD uint32_t src_index(uint32_t i, uint32_t dist) { return i < dist ? i : i % dist; }
+// the same when the caller already knows (warp-uniformly) that the match does not overlap itself
+LZ_HD uint32_t src_index_far(uint32_t i) { return i; }
 
 }  // namespace lzgpu

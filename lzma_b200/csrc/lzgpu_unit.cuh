@@ -76,15 +76,15 @@ LZ_DEV void set_props(Dec &d, uint32_t lc, uint32_t lp, uint32_t pb) {
 // Decode symbols until the range-coded part ends (Reader1.Read driving
 // decompress(), reader1.go:223-254).  On return d.status / d.site are set and no
 // store is pending.
+template <int kV>
 LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8_t *dict_base) {
     for (;;) {
         uint32_t op = OP_DONE, len = 0, dist = 0;
         uint64_t dstbits = 0;
         LZ_IF_LANE0 {
-            op = decode_run(d, P, L, len, dist);
+            op = decode_run<kV>(d, P, L, len, dist);
             dstbits = (uint64_t)(uintptr_t)d.outp;
         }
-        LZ_SYNC();
         uint32_t pk = op | (len << 2);
         LZ_BCAST32(pk);
         op = pk & 3u;
@@ -97,26 +97,27 @@ LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8
         wc_commit(wc);  // the previous match's bytes reach memory before anything reads them
 
         if (op == OP_COPY) {
+            // dist > len (warp-uniform): no byte of the match depends on the match itself and
+            // byte i simply comes from dst[i - dist]; otherwise the source repeats with period dist.
+            const bool far = dist > len;
+            const uint8_t *src = dst - dist;
             if (len <= 32) {
                 // deferred: load now, store at the next commit
                 LZ_FOR_LANES(l) {
-                    if (l < len) LZ_LV(wc.pend_val, l) = dst[(int64_t)src_index(l, dist) - (int64_t)dist];
+                    if (l < len) LZ_LV(wc.pend_val, l) = src[far ? l : src_index(l, dist)];
                 }
                 wc.pend_len = len;
                 wc.pend_dst = dst;
             } else {
                 LZ_FOR_LANES(l) {
-                    for (uint32_t i = l; i < len; i += 32) {
-                        const uint8_t v = dst[(int64_t)src_index(i, dist) - (int64_t)dist];
-                        dst[i] = v;
-                    }
+                    for (uint32_t i = l; i < len; i += 32) dst[i] = src[far ? i : src_index(i, dist)];
                 }
             }
             LZ_IF_LANE0 {
                 // context for a literal / short rep that may follow: the last byte of the
                 // match and the byte at -(rep0+1) after it.  Both predate the match.
-                d.prev_byte = dst[(int64_t)src_index(len - 1, dist) - (int64_t)dist];
-                d.mbyte = dst[(int64_t)src_index(len, dist) - (int64_t)dist];
+                d.prev_byte = src[far ? len - 1 : src_index(len - 1, dist)];
+                d.mbyte = src[far ? len : src_index(len, dist)];
                 d.outp = dst + len;
             }
         } else {  // OP_COPY_Q4: dist == bytes since dictionary start + 1; byte "-1" reads as 0
@@ -154,6 +155,7 @@ struct UnitIO {
 };
 
 // LZMA1 unit (kind RAW; ALONE units are converted by the host).
+template <int kV>
 LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, uint16_t *L,
                            lzgpu_result &res) {
     Dec d;
@@ -181,7 +183,7 @@ LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     LZ_BCAST32(r);
     if (r < 0) { d.status = LZGPU_UNEXPECTED_EOF; }                       // "rangeDec.Init: %w" of io.EOF
     else if (r > 0) { d.status = LZGPU_RESULT_ERROR; d.site = LZGPU_SITE_RC_INIT; }
-    else run_lzma(d, wc, P, L, io.out);
+    else run_lzma<kV>(d, wc, P, L, io.out);
 
     LZ_IF_LANE0 {
         res.status = d.status;
@@ -193,6 +195,7 @@ LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
 }
 
 // LZMA2 group: walk the chunks (Reader2.startChunk + Read, reader2.go:100-250).
+template <int kV>
 LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, uint16_t *L,
                            uint32_t lit_bits_cap, lzgpu_result &res) {
     Dec d;
@@ -341,7 +344,7 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
             break;
         }
         reload_context(d, dict_base);
-        run_lzma(d, wc, P, L, dict_base);
+        run_lzma<kV>(d, wc, P, L, dict_base);
 
         // what the chunk did, as seen by every lane
         uint32_t st = (uint32_t)d.status, st_site = (uint32_t)d.site, complete = 0, exact = 0;

@@ -22,12 +22,15 @@ def emu_lib():
         _EMU = C.CDLL(os.path.join(here, "emu", "_build", "liblzgpu_emu.so"))
         _EMU.emu_decode_batch.restype = C.c_int
         _EMU.emu_decode_batch.argtypes = [C.POINTER(Unit), C.c_int64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
-                                          C.POINTER(Result)]
+                                          C.POINTER(Result), C.c_int]
     return _EMU
 
 
 class EmuContext:
     n_devices = 1
+
+    def __init__(self, variant: int = 2):
+        self.variant = variant
 
     def decode_batch(self, units, in_buf: np.ndarray, out_buf: np.ndarray):
         n = len(units)
@@ -46,7 +49,7 @@ class EmuContext:
         sub = (Unit * max(len(run), 1))(*[arr[i] for i in run])
         sres = (Result * max(len(run), 1))()
         rc = emu_lib().emu_decode_batch(sub, len(run), in_buf.ctypes.data, in_buf.nbytes, out_buf.ctypes.data,
-                                        out_buf.nbytes, sres)
+                                        out_buf.nbytes, sres, self.variant)
         assert rc == 0, rc
         for k, i in enumerate(run):
             res[i] = sres[k]
@@ -59,8 +62,8 @@ class EmuContext:
         pass
 
 
-def make_context(kind: str):
+def make_context(kind: str, variant: int = 2):
     if kind == "emu":
-        return EmuContext()
+        return EmuContext(variant)
     from lzma_b200.batch import Context
     return Context()

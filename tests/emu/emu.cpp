@@ -18,8 +18,14 @@
 
 using namespace lzgpu;
 
+template <int kV>
+static void run_one(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, uint16_t *L, uint32_t bits, lzgpu_result &r) {
+    if (u.kind == LZGPU_KIND_LZMA2_GROUP) run_unit_lzma2<kV>(u, io, P, L, bits, r);
+    else run_unit_lzma1<kV>(u, io, P, L, r);
+}
+
 extern "C" int emu_decode_batch(const lzgpu_unit *units, int64_t n, const uint8_t *in_base, uint64_t in_size,
-                                uint8_t *out_base, uint64_t out_size, lzgpu_result *results) {
+                                uint8_t *out_base, uint64_t out_size, lzgpu_result *results, int variant) {
     for (int64_t i = 0; i < n; i++) {
         lzgpu_unit u = units[i];
         if (u.in_off > in_size || u.in_len > in_size - u.in_off || u.out_off > out_size || u.out_cap > out_size - u.out_off)
@@ -36,8 +42,13 @@ extern "C" int emu_decode_batch(const lzgpu_unit *units, int64_t n, const uint8_
         io.out_cap = u.out_cap;
         memset(&r, 0, sizeof r);
         r.status = LZGPU_NOT_RUN;
-        if (u.kind == LZGPU_KIND_LZMA2_GROUP) run_unit_lzma2(u, io, probs.data(), probs.data() + P_LIT, bits, r);
-        else run_unit_lzma1(u, io, probs.data(), probs.data() + P_LIT, r);
+        uint16_t *P = probs.data(), *L = probs.data() + P_LIT;
+        switch (variant) {
+            case 1: run_one<1>(u, io, P, L, bits, r); break;
+            case 2: run_one<2>(u, io, P, L, bits, r); break;
+            case 3: run_one<3>(u, io, P, L, bits, r); break;
+            default: run_one<0>(u, io, P, L, bits, r); break;
+        }
         if (alone) r.bytes_in += 13;
         r.device = -1;
         results[i] = r;

@@ -12,9 +12,10 @@ from lzma_b200 import batch as B
 from oracle import oracle as O
 
 
-@pytest.fixture(scope="module")
-def ctx():
-    return make_context("emu")
+@pytest.fixture(scope="module", params=[0, 1, 2, 3])
+def ctx(request):
+    """Every tuning variant of the decoder (lzgpu_core.cuh V_*) must give identical results."""
+    return make_context("emu", request.param)
 
 
 def test_alone_cases(ctx):

@@ -109,3 +109,17 @@ def test_large_literal_tables_in_hbm(ctx):
         want = O.lzma_alone(t, 200_000)
         g = B.decode_alone_streams(ctx, [t], [200_000])[0]
         same_outcome(want, g.status, g.err_site, g.data, f"prop{prop}")
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_tuning_variants_agree(variant, monkeypatch):
+    """Every decoder tuning variant (LZGPU_VARIANT, lzgpu_core.cuh V_*) is bit-exact."""
+    monkeypatch.setenv("LZGPU_VARIANT", str(variant))
+    with B.Context([0]) as c:
+        cs = cases.alone_cases(heavy=False)
+        got = B.decode_alone_streams(c, [x[1] for x in cs], [x[2] for x in cs])
+        for (name, s, cap), g in zip(cs, got):
+            same_outcome(O.lzma_alone(s, cap), g.status, g.err_site, g.data, f"v{variant}:{name}")
+        for name, s, dict_size, cap in cases.lzma2_cases()[:6]:
+            st, site, data = B.decode_lzma2_stream(c, s, dict_size)
+            same_outcome(O.lzma2(s, dict_size, cap + (1 << 20)), st, site, data, f"v{variant}:{name}", strict_site=False)
