@@ -24,7 +24,7 @@
 using namespace lzgpu;
 
 #ifndef LZGPU_DEFAULT_VARIANT
-#define LZGPU_DEFAULT_VARIANT 2
+#define LZGPU_DEFAULT_VARIANT 3
 #endif
 
 // ------------------------------------------------------------------ kernel

@@ -37,6 +37,12 @@
 #define LZ_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #define LZ_FUNNEL_L(lo, hi, sh) __funnelshift_l((lo), (hi), (sh))   /* ((hi:lo) << sh) >> 32, sh < 32 */
 #define LZ_CLZ(x) ((uint32_t)__clz((int)(x)))
+#define LZ_FUNNEL_R(lo, hi, sh) __funnelshift_r((lo), (hi), (sh))   /* ((hi:lo) >> (sh & 31)) low word */
+#define LZ_SHR_CLAMP(x, sh) __funnelshift_rc((x), 0u, (sh))          /* x >> min(sh, 32) */
+// predicated global load: no branch, so lane 0's instruction stream stays straight-line
+#define LZ_LD_IN32_IF(dst, p, cond)                                                     \
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}" \
+                 : "+r"(dst) : "l"(p), "r"((uint32_t)(cond)))
 #define LZ_LIKELY(x) __builtin_expect(!!(x), 1)
 #define LZ_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #else
@@ -46,6 +52,9 @@
 #define LZ_PREFETCH_L2(p) ((void)0)
 #define LZ_FUNNEL_L(lo, hi, sh) ((uint32_t)(((((uint64_t)(hi)) << 32 | (uint64_t)(lo)) << (sh)) >> 32))
 #define LZ_CLZ(x) ((uint32_t)__builtin_clz(x))
+#define LZ_FUNNEL_R(lo, hi, sh) ((uint32_t)(((((uint64_t)(hi)) << 32 | (uint64_t)(lo)) >> ((sh) & 31))))
+#define LZ_SHR_CLAMP(x, sh) ((sh) >= 32 ? 0u : ((uint32_t)(x) >> (sh)))
+#define LZ_LD_IN32_IF(dst, p, cond) do { if (cond) (dst) = *(const uint32_t *)(p); } while (0)
 #define LZ_LIKELY(x) __builtin_expect(!!(x), 1)
 #define LZ_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #endif
@@ -72,7 +81,7 @@ constexpr uint32_t kTop = 1u << 24;
 constexpr uint32_t kProbInit = 1024;
 
 // what lane 0 hands to the warp when it leaves decode_run()
-enum : uint32_t { OP_COPY = 0, OP_COPY_Q4 = 1, OP_DONE = 2 };
+enum : uint32_t { OP_COPY = 0, OP_COPY_Q4 = 1, OP_DONE = 2, OP_SWITCH = 3 };
 
 // Lane 0's decoder registers.
 struct Dec {
@@ -81,10 +90,13 @@ struct Dec {
     uint32_t inbits;                // bits in the lookahead (real bytes first, then phantom zeros)
     uint32_t phantom;               // zero BITS appended after the real input ran out
     const uint8_t *ip, *in_end;     // next byte to load / end of the real input
+    uint32_t nextw;                 // fast mode: the aligned word at ip-4, loaded ahead, not yet appended
     uint32_t rep0, rep1, rep2, rep3, state;
     uint32_t wpos, dict_size;       // window.pos (wrapped, Q3) and window.size
     uint32_t full;                  // window.isFull
     uint8_t *outp, *out_end;        // write cursor; out_end = start + min(size, cap)
+    const uint8_t *fast_in_end;     // fast decoder may start a symbol while ip <= fast_in_end ...
+    uint8_t *fast_out_end;          // ... and outp <= fast_out_end
     uint32_t end_is_size;           // out_end is the declared unpack size (else the caller's cap)
     uint32_t size_defined;          // state.unpackSizeDefined
     uint32_t lc, lp_mask, pos_mask;
@@ -129,15 +141,36 @@ LZ_HD void rc_fill(Dec &d) {
         d.inbits = 32;
     }
 }
-// Tuning variants (template parameter kV of decode_run; chosen per launch):
-//   V_NORM_BRANCH  normalise under a rarely-taken branch that also tops up the lookahead
-//                  (fewer instructions per bit, one convergence-barrier pair per bit);
-//                  otherwise normalise with selects and top up at LZ_FILL() points
+// decode_run<kV, kFast>.
+//  kFast: the straight-line decoder used while >= kFastInMargin input bytes and
+//         >= kFastOutMargin output bytes remain (one symbol can never need more): no input
+//         exhaustion, no size/capacity checks, and the lookahead is topped up WITHOUT a branch from a
+//         word that was loaded one top-up earlier.  Taken branches cost a lone warp an
+//         instruction-fetch bubble each (ncu: stall_no_instructions), hence the effort.
+//         The careful decoder (kFast = false) handles the head and tail of a unit.
+//  kV tuning variants, chosen per launch:
+//   V_FAST         allow the fast decoder at all
 //   V_DIRECT_GROUP equiprobable bits in runs between two normalisations (their position is
 //                  known from the range's leading zeros) instead of a full step per bit
-enum : int { V_NORM_BRANCH = 1, V_DIRECT_GROUP = 2 };
+enum : int { V_FAST = 1, V_DIRECT_GROUP = 2 };
+constexpr uint32_t kFastInMargin = 64;    // >= 48 bit steps of one symbol + one word loaded ahead + slack
+constexpr uint32_t kFastOutMargin = 274;  // longest match is 273
+
 #define LZ_FILL32() do { if (LZ_UNLIKELY(d.inbits < 32)) rc_fill(d); } while (0)
-#define LZ_FILL() do { if (!(kV & V_NORM_BRANCH)) LZ_FILL32(); } while (0)
+#define LZ_FILL()                                                                   \
+    do {                                                                            \
+        if (kFast) {                                                                \
+            const bool f_ = d.inbits < 32;      /* then inb_lo == 0 */             \
+            const uint32_t w_ = LZ_BSWAP32(d.nextw);                                \
+            d.inb_hi |= LZ_SHR_CLAMP(w_, d.inbits);   /* adds nothing when inbits >= 32 */ \
+            d.inb_lo = f_ ? LZ_FUNNEL_R(0u, w_, d.inbits) : d.inb_lo;               \
+            d.inbits += f_ ? 32u : 0u;                                              \
+            LZ_LD_IN32_IF(d.nextw, d.ip, f_);                                       \
+            d.ip += f_ ? 4 : 0;                                                     \
+        } else {                                                                    \
+            LZ_FILL32();                                                            \
+        }                                                                           \
+    } while (0)
 #define LZ_SHIFT8()                                                                 \
     do {                                                                            \
         d.range <<= 8;                                                              \
@@ -146,12 +179,24 @@ enum : int { V_NORM_BRANCH = 1, V_DIRECT_GROUP = 2 };
         d.inb_lo <<= 8;                                                             \
         d.inbits -= 8;                                                              \
     } while (0)
-#define LZ_EXHAUSTED() (d.phantom > d.inbits)
+#define LZ_EXHAUSTED() (!kFast && d.phantom > d.inbits)
 
 // real input bytes consumed so far, given the start of the input
 LZ_HD uint64_t rc_consumed(const Dec &d, const uint8_t *start) {
     const uint32_t unread = d.inbits > d.phantom ? (d.inbits - d.phantom) >> 3 : 0;
     return (uint64_t)(d.ip - start) - unread;
+}
+
+// May the fast decoder start a symbol here?  (ip is where the careful decoder loads next;
+// the fast one keeps one more word loaded ahead, hence the +4.)
+LZ_HD bool fast_possible(const Dec &d) {
+    return ((uintptr_t)d.ip & 3u) == 0 && d.phantom == 0 && d.ip + 4 <= d.fast_in_end && d.outp <= d.fast_out_end;
+}
+LZ_HD void set_fast_limits(Dec &d) {
+    d.fast_in_end = d.in_end - kFastInMargin;
+    d.fast_out_end = d.out_end - kFastOutMargin;
+    if ((uint64_t)(d.in_end - d.ip) < kFastInMargin + 8) d.fast_in_end = d.ip - 8;   // never
+    if ((uint64_t)(d.out_end - d.outp) < kFastOutMargin) d.fast_out_end = d.outp - 1;  // never
 }
 
 // Range-coder preamble: rangeDecoder.Init, range_decoder.go:27-46.
@@ -176,19 +221,12 @@ LZ_HD int rc_init(Dec &d) {
 // no branch, so no convergence barrier and no fetch bubble in lane 0's instruction stream.
 #define LZ_NORM()                                                                   \
     do {                                                                            \
-        if (kV & V_NORM_BRANCH) {                                                   \
-            if (LZ_UNLIKELY(d.range < kTop)) {                                      \
-                if (LZ_UNLIKELY(d.inbits < 8)) rc_fill(d);                          \
-                LZ_SHIFT8();                                                        \
-            }                                                                       \
-        } else {                                                                    \
-            const uint32_t sh_ = d.range < kTop ? 8u : 0u;                          \
-            d.range <<= sh_;                                                        \
-            d.code = LZ_FUNNEL_L(d.inb_hi, d.code, sh_);                            \
-            d.inb_hi = LZ_FUNNEL_L(d.inb_lo, d.inb_hi, sh_);                        \
-            d.inb_lo <<= sh_;                                                       \
-            d.inbits -= sh_;                                                        \
-        }                                                                           \
+        const uint32_t sh_ = d.range < kTop ? 8u : 0u;                              \
+        d.range <<= sh_;                                                            \
+        d.code = LZ_FUNNEL_L(d.inb_hi, d.code, sh_);                                \
+        d.inb_hi = LZ_FUNNEL_L(d.inb_lo, d.inb_hi, sh_);                            \
+        d.inb_lo <<= sh_;                                                           \
+        d.inbits -= sh_;                                                            \
     } while (0)
 
 // One adaptive bit (DecodeBit, range_decoder.go:57-98), select form.
@@ -284,10 +322,17 @@ LZ_HD int rc_init(Dec &d) {
 // short rep: OP_COPY or OP_COPY_Q4 with len and dist set, window position already
 // advanced) or the unit part ends (OP_DONE with d.status / d.site set).
 // P: fixed tables (shared memory), L: literal tables (shared or global).
-template <int kV>
+template <int kV, bool kFast>
 LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, uint32_t &out_dist) {
     for (;;) {
-        const bool at_end = (d.outp == d.out_end);
+        // fast decoder: leave when the margins are gone (at_end is then impossible);
+        // careful decoder: hand over as soon as the fast one may run
+        if (kFast) {
+            if (LZ_UNLIKELY(d.ip > d.fast_in_end || d.outp > d.fast_out_end)) return OP_SWITCH;
+        } else if ((kV & V_FAST) && fast_possible(d)) {
+            return OP_SWITCH;
+        }
+        const bool at_end = !kFast && (d.outp == d.out_end);
         // decompress.go:14-20
         if (at_end && d.end_is_size && d.code == 0) LZ_FAIL(LZGPU_OK, 0);
 
@@ -438,8 +483,9 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
         if (LZ_UNLIKELY(LZ_EXHAUSTED())) goto input_eof;
 
         // copy: decompress.go:656-668 / :934-947 / :1028-1041 / :1104-1117
-        const uint64_t avail = (uint64_t)(d.out_end - d.outp);
-        if (d.end_is_size) {
+        const uint64_t avail = kFast ? ~(uint64_t)0 : (uint64_t)(d.out_end - d.outp);
+        if (kFast) {
+        } else if (d.end_is_size) {
             if (LZ_UNLIKELY((uint32_t)avail < len)) LZ_FAIL(LZGPU_RESULT_ERROR, trunc_site);  // uint32(bytesLeft) < length (Q10)
         } else if (LZ_UNLIKELY(avail < len)) {
             LZ_FAIL(LZGPU_OUTPUT_OVERFLOW, 0);

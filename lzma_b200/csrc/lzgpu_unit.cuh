@@ -78,11 +78,26 @@ LZ_DEV void set_props(Dec &d, uint32_t lc, uint32_t lp, uint32_t pb) {
 // store is pending.
 template <int kV>
 LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8_t *dict_base) {
+    bool fast = false;   // lane 0: which decoder runs (lzgpu_core.cuh, kFast)
+    set_fast_limits(d);
     for (;;) {
         uint32_t op = OP_DONE, len = 0, dist = 0;
         uint64_t dstbits = 0;
         LZ_IF_LANE0 {
-            op = decode_run<kV>(d, P, L, len, dist);
+            for (;;) {
+                if (fast) {
+                    op = decode_run<kV, true>(d, P, L, len, dist);
+                    if (op != OP_SWITCH) break;
+                    d.ip -= 4;                       // forget the word loaded ahead
+                    fast = false;
+                } else {
+                    op = decode_run<kV, false>(d, P, L, len, dist);
+                    if (op != OP_SWITCH) break;
+                    d.nextw = LZ_LD_IN32(d.ip);      // fast decoder keeps one aligned word in hand
+                    d.ip += 4;
+                    fast = true;
+                }
+            }
             dstbits = (uint64_t)(uintptr_t)d.outp;
         }
         uint32_t pk = op | (len << 2);
@@ -133,6 +148,9 @@ LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8
             }
             LZ_SYNC();
         }
+    }
+    LZ_IF_LANE0 {
+        if (fast) d.ip -= 4;   // the word loaded ahead was never consumed
     }
     wc_commit(wc);
 }
