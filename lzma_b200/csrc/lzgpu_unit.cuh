@@ -114,26 +114,44 @@ LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8
         if (op == OP_COPY) {
             // dist > len (warp-uniform): no byte of the match depends on the match itself and
             // byte i simply comes from dst[i - dist]; otherwise the source repeats with period dist.
-            const bool far = dist > len;
             const uint8_t *src = dst - dist;
-            if (len <= 32) {
-                // deferred: load now, store at the next commit
-                LZ_FOR_LANES(l) {
-                    if (l < len) LZ_LV(wc.pend_val, l) = src[far ? l : src_index(l, dist)];
+            if (LZ_LIKELY(dist > len)) {
+                if (len <= 32) {
+                    // deferred: load now, store at the next commit
+                    LZ_FOR_LANES(l) {
+                        if (l < len) LZ_LV(wc.pend_val, l) = src[l];
+                    }
+                    wc.pend_len = len;
+                    wc.pend_dst = dst;
+                } else {
+                    LZ_FOR_LANES(l) {
+                        for (uint32_t i = l; i < len; i += 32) dst[i] = src[i];
+                    }
                 }
-                wc.pend_len = len;
-                wc.pend_dst = dst;
-            } else {
-                LZ_FOR_LANES(l) {
-                    for (uint32_t i = l; i < len; i += 32) dst[i] = src[far ? i : src_index(i, dist)];
+                LZ_IF_LANE0 {
+                    // context for a literal / short rep that may follow: the last byte of the
+                    // match and the byte at -(rep0+1) after it.  Both predate the match.
+                    d.prev_byte = src[len - 1];
+                    d.mbyte = src[len];
+                    d.outp = dst + len;
                 }
-            }
-            LZ_IF_LANE0 {
-                // context for a literal / short rep that may follow: the last byte of the
-                // match and the byte at -(rep0+1) after it.  Both predate the match.
-                d.prev_byte = src[far ? len - 1 : src_index(len - 1, dist)];
-                d.mbyte = src[far ? len : src_index(len, dist)];
-                d.outp = dst + len;
+            } else {  // the match overlaps itself: period-dist replication (window.go:73-86)
+                if (len <= 32) {
+                    LZ_FOR_LANES(l) {
+                        if (l < len) LZ_LV(wc.pend_val, l) = src[src_index(l, dist)];
+                    }
+                    wc.pend_len = len;
+                    wc.pend_dst = dst;
+                } else {
+                    LZ_FOR_LANES(l) {
+                        for (uint32_t i = l; i < len; i += 32) dst[i] = src[src_index(i, dist)];
+                    }
+                }
+                LZ_IF_LANE0 {
+                    d.prev_byte = src[src_index(len - 1, dist)];
+                    d.mbyte = src[src_index(len, dist)];
+                    d.outp = dst + len;
+                }
             }
         } else {  // OP_COPY_Q4: dist == bytes since dictionary start + 1; byte "-1" reads as 0
             LZ_IF_LANE0 {
