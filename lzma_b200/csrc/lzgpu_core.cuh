@@ -152,7 +152,9 @@ LZ_HD void rc_fill(Dec &d) {
 //   V_FAST         allow the fast decoder at all
 //   V_DIRECT_GROUP equiprobable bits in runs between two normalisations (their position is
 //                  known from the range's leading zeros) instead of a full step per bit
-enum : int { V_FAST = 1, V_DIRECT_GROUP = 2 };
+//   V_PREFETCH     bit trees load BOTH children of the current node (one aligned 32-bit LDS)
+//                  before the bit is known, so the shared-memory latency leaves the serial chain
+enum : int { V_FAST = 1, V_DIRECT_GROUP = 2, V_PREFETCH = 4 };
 constexpr uint32_t kFastInMargin = 64;    // >= 48 bit steps of one symbol + one word loaded ahead + slack
 constexpr uint32_t kFastOutMargin = 274;  // longest match is 273
 
@@ -245,6 +247,19 @@ LZ_HD int rc_init(Dec &d) {
         LZ_NORM();                                                                  \
     } while (0)
 
+// The same with the probability value already in a register (prefetched); PP is where to store it.
+#define LZ_BIT_P(PP, PVAL, BIT)                                                     \
+    do {                                                                            \
+        const uint32_t p_ = (PVAL);                                                 \
+        const uint32_t bound_ = (d.range >> 11) * p_;                               \
+        const bool one_ = d.code >= bound_;                                         \
+        d.range = one_ ? d.range - bound_ : bound_;                                 \
+        d.code = one_ ? d.code - bound_ : d.code;                                   \
+        *(PP) = (uint16_t)(p_ + (uint32_t)((int32_t)((one_ ? 31u : 2048u) - p_) >> 5)); \
+        (BIT) = one_ ? 1u : 0u;                                                     \
+        LZ_NORM();                                                                  \
+    } while (0)
+
 // One equiprobable bit (DecodeDirectBits, range_decoder.go:100-134 / decompress.go:549-576)
 #define LZ_DIRECT(RES)                                                              \
     do {                                                                            \
@@ -255,32 +270,64 @@ LZ_HD int rc_init(Dec &d) {
         LZ_NORM();                                                                  \
     } while (0)
 
+// Children of node m are entries 2m and 2m+1: one aligned 32-bit load when the table base is
+// 4-byte aligned (all P_* bases and sub-table strides are even).
+#define LZ_PAIR(TP, M) (*reinterpret_cast<const uint32_t *>((TP) + 2u * (M)))
+#define LZ_PICK(PAIR, BIT) ((BIT) ? ((PAIR) >> 16) : ((PAIR) & 0xFFFFu))
+
 // MSB-first bit tree (BitTreeDecode, bit_tree_decoder.go:26-76), NBITS constant, unrolled.
 // FILL_AT: a fill is issued before bit i whenever (i & 3) == FILL_AT (keeps <= 4 steps per fill).
 #define LZ_TREE(PROBS, NBITS, OUT, FILL_AT)                                         \
     do {                                                                            \
         uint16_t *tp_ = (PROBS);                                                    \
         uint32_t m_ = 1, b_;                                                        \
-        _Pragma("unroll") for (int i_ = 0; i_ < (NBITS); i_++) {                    \
-            if ((i_ & 3) == (FILL_AT)) LZ_FILL();                                   \
-            LZ_BIT(tp_ + m_, b_);                                                   \
-            m_ = (m_ << 1) | b_;                                                    \
+        if (kV & V_PREFETCH) {                                                      \
+            uint32_t pv_ = tp_[1];                                                  \
+            _Pragma("unroll") for (int i_ = 0; i_ < (NBITS); i_++) {                \
+                if ((i_ & 3) == (FILL_AT)) LZ_FILL();                               \
+                uint32_t pair_ = 0;                                                 \
+                if (i_ + 1 < (NBITS)) pair_ = LZ_PAIR(tp_, m_);                     \
+                LZ_BIT_P(tp_ + m_, pv_, b_);                                        \
+                m_ = (m_ << 1) | b_;                                                \
+                pv_ = LZ_PICK(pair_, b_);                                           \
+            }                                                                       \
+        } else {                                                                    \
+            _Pragma("unroll") for (int i_ = 0; i_ < (NBITS); i_++) {                \
+                if ((i_ & 3) == (FILL_AT)) LZ_FILL();                               \
+                LZ_BIT(tp_ + m_, b_);                                               \
+                m_ = (m_ << 1) | b_;                                                \
+            }                                                                       \
         }                                                                           \
         (OUT) = m_ - (1u << (NBITS));                                               \
     } while (0)
 
-// LSB-first bit tree (BitTreeReverseDecode, bit_tree_decoder.go:82-135), runtime NBITS <= 5
+// LSB-first bit tree (BitTreeReverseDecode, bit_tree_decoder.go:82-135), runtime NBITS <= MAXBITS
 #define LZ_TREE_REV(PROBS, NBITS, OUT, MAXBITS)                                     \
     do {                                                                            \
         uint16_t *tp_ = (PROBS);                                                    \
         uint32_t m_ = 1, b_, s_ = 0;                                                \
         const uint32_t nb_ = (NBITS);                                               \
-        _Pragma("unroll") for (uint32_t i_ = 0; i_ < (MAXBITS); i_++) {             \
-            if (i_ < nb_) {                                                         \
-                if (i_ == 4) LZ_FILL();                                             \
-                LZ_BIT(tp_ + m_, b_);                                               \
-                m_ = (m_ << 1) | b_;                                                \
-                s_ |= b_ << i_;                                                     \
+        if (kV & V_PREFETCH) {                                                      \
+            uint32_t pv_ = tp_[1];                                                  \
+            _Pragma("unroll") for (uint32_t i_ = 0; i_ < (MAXBITS); i_++) {         \
+                if (i_ < nb_) {                                                     \
+                    if (i_ == 4) LZ_FILL();                                         \
+                    uint32_t pair_ = 0;                                             \
+                    if (i_ + 1 < nb_) pair_ = LZ_PAIR(tp_, m_);               \
+                    LZ_BIT_P(tp_ + m_, pv_, b_);                                    \
+                    m_ = (m_ << 1) | b_;                                            \
+                    s_ |= b_ << i_;                                                 \
+                    pv_ = LZ_PICK(pair_, b_);                                       \
+                }                                                                   \
+            }                                                                       \
+        } else {                                                                    \
+            _Pragma("unroll") for (uint32_t i_ = 0; i_ < (MAXBITS); i_++) {         \
+                if (i_ < nb_) {                                                     \
+                    if (i_ == 4) LZ_FILL();                                         \
+                    LZ_BIT(tp_ + m_, b_);                                           \
+                    m_ = (m_ << 1) | b_;                                            \
+                    s_ |= b_ << i_;                                                 \
+                }                                                                   \
             }                                                                       \
         }                                                                           \
         (OUT) = s_;                                                                 \
@@ -392,7 +439,9 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
                 uint32_t dist = (2 | (slot & 1)) << nd, v;
                 LZ_FILL();
                 if (slot < 14) {                                  // :494-546
-                    LZ_TREE_REV(P + P_POS_DEC + dist - slot, nd, v, 5);
+                    // own sub-table layout: slot s starts at dist - 4 (always even, so that a node's
+                    // two children share an aligned word); the reference's is dist - slot (:496)
+                    LZ_TREE_REV(P + P_POS_DEC + dist - 4, nd, v, 5);
                     dist += v;
                 } else {                                          // :548-628
                     uint32_t res = 0;
@@ -400,20 +449,28 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
                         // DecodeDirectBits (:549-576) normalises when the halved range drops below
                         // 2^24: first after g = 8 - clz(range) halvings, then after every 8th.
                         // At most 4 normalisations for 26 bits: one top-up covers them.
-                        LZ_FILL32();
-                        uint32_t n = nd - 4;
-                        uint32_t g = 8 - LZ_CLZ(d.range);
+                        if (kFast) LZ_FILL(); else LZ_FILL32();
+                        uint32_t n = nd - 4;                       // 1..26
+                        uint32_t g = 8 - LZ_CLZ(d.range);          // 1..8 halvings to the next normalisation
+#pragma unroll 1
                         for (;;) {
-                            uint32_t k = n < g ? n : g;
-                            n -= k;
-                            g -= k;
-                            for (; k > 0; k--) {
-                                d.range >>= 1;
-                                const bool one = d.code >= d.range;
-                                d.code -= one ? d.range : 0u;
-                                res = (res << 1) | (one ? 1u : 0u);
+                            const uint32_t k = n < g ? n : g;
+                            // k halvings without normalisation: step j compares against range >> j
+                            // (floor of floor = floor), so only `code` carries from step to step
+                            const uint32_t r0 = d.range;
+                            uint32_t acc = 0;
+#pragma unroll
+                            for (uint32_t j = 1; j <= 8; j++) {
+                                const uint32_t rj = r0 >> j;
+                                const bool one = (j <= k) && d.code >= rj;
+                                d.code -= one ? rj : 0u;
+                                acc |= one ? (1u << (8 - j)) : 0u;
                             }
-                            if (g == 0) { LZ_SHIFT8(); g = 8; }
+                            d.range = r0 >> k;
+                            res = (res << k) | (acc >> (8 - k));
+                            n -= k;
+                            if (k == g) LZ_SHIFT8();
+                            g = 8;
                             if (n == 0) break;
                         }
                     } else {
