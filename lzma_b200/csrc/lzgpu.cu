@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(32) lzgpu_decode_kernel(const KArgs a) {
 // overrides the default; read once per plan.
 static int decoder_variant() {
     const char *e = getenv("LZGPU_VARIANT");
-    if (e && *e >= '0' && *e <= '7') return *e - '0';
+    if (e && *e >= '0' && *e <= '9') return atoi(e);
     return LZGPU_DEFAULT_VARIANT;
 }
 
@@ -75,6 +75,7 @@ static void launch_decode(int variant, unsigned grid, size_t smem, cudaStream_t 
         case 2: lzgpu_decode_kernel<kLitGlobal, 2><<<grid, 32, smem, st>>>(a); break;
         case 3: lzgpu_decode_kernel<kLitGlobal, 3><<<grid, 32, smem, st>>>(a); break;
         case 7: lzgpu_decode_kernel<kLitGlobal, 7><<<grid, 32, smem, st>>>(a); break;
+        case 11: lzgpu_decode_kernel<kLitGlobal, 11><<<grid, 32, smem, st>>>(a); break;
         default: lzgpu_decode_kernel<kLitGlobal, 0><<<grid, 32, smem, st>>>(a); break;
     }
 }

@@ -154,7 +154,10 @@ LZ_HD void rc_fill(Dec &d) {
 //                  known from the range's leading zeros) instead of a full step per bit
 //   V_PREFETCH     bit trees load BOTH children of the current node (one aligned 32-bit LDS)
 //                  before the bit is known, so the shared-memory latency leaves the serial chain
-enum : int { V_FAST = 1, V_DIRECT_GROUP = 2, V_PREFETCH = 4 };
+//   V_UNIFORM      all 32 lanes run the serial decoder redundantly on identical data instead of
+//                  lane 0 alone: same issue cost (SIMT), but no divergence entry/exit and no
+//                  shuffles per match; same-address shared/global accesses are broadcasts
+enum : int { V_FAST = 1, V_DIRECT_GROUP = 2, V_PREFETCH = 4, V_UNIFORM = 8 };
 constexpr uint32_t kFastInMargin = 64;    // >= 48 bit steps of one symbol + one word loaded ahead + slack
 constexpr uint32_t kFastOutMargin = 274;  // longest match is 273
 

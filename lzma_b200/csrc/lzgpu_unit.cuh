@@ -17,16 +17,19 @@
 #if defined(__CUDA_ARCH__)
 #define LZ_LANE() (threadIdx.x & 31u)
 #define LZ_FOR_LANES(l) for (uint32_t l = LZ_LANE(), once_ = 1; once_; once_ = 0)
-#define LZ_IF_LANE0 if (LZ_LANE() == 0)
+// the serial decoder runs on lane 0 only, or (V_UNIFORM) redundantly on every lane
+#define LZ_IF_LANE0 if ((kV & V_UNIFORM) || LZ_LANE() == 0)
+#define LZ_IF_LANE0_ONLY if (LZ_LANE() == 0)
 #define LZ_SYNC() __syncwarp()
-#define LZ_BCAST32(x) ((x) = __shfl_sync(0xffffffffu, (x), 0))
-#define LZ_BCAST64(x) ((x) = __shfl_sync(0xffffffffu, (x), 0))
+#define LZ_BCAST32(x) do { if (!(kV & V_UNIFORM)) (x) = __shfl_sync(0xffffffffu, (x), 0); } while (0)
+#define LZ_BCAST64(x) do { if (!(kV & V_UNIFORM)) (x) = __shfl_sync(0xffffffffu, (x), 0); } while (0)
 #define LZ_LANEVAR(T, name) T name
 #define LZ_LV(name, l) name
 #define LZ_DEV __device__ __forceinline__
 #else
 #define LZ_FOR_LANES(l) for (uint32_t l = 0; l < 32; l++)
 #define LZ_IF_LANE0
+#define LZ_IF_LANE0_ONLY
 #define LZ_SYNC() ((void)0)
 #define LZ_BCAST32(x) ((void)0)
 #define LZ_BCAST64(x) ((void)0)
@@ -175,6 +178,7 @@ LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8
 
 // Reload the literal context from memory (window.GetByte(1) / GetByte(rep0+1),
 // decompress.go:50-60) when the decoder (re)starts at a position it did not write.
+template <int kV>
 LZ_DEV void reload_context(Dec &d, const uint8_t *dict_base) {
     LZ_IF_LANE0 {
         const uint64_t hist = (uint64_t)(d.outp - dict_base);
@@ -221,7 +225,7 @@ LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     else if (r > 0) { d.status = LZGPU_RESULT_ERROR; d.site = LZGPU_SITE_RC_INIT; }
     else run_lzma<kV>(d, wc, P, L, io.out);
 
-    LZ_IF_LANE0 {
+    LZ_IF_LANE0_ONLY {
         res.status = d.status;
         res.err_site = d.site;
         res.bytes_out = (uint64_t)(d.outp - io.out);
@@ -379,7 +383,7 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
             else { status = LZGPU_RESULT_ERROR; site = LZGPU_SITE_RC_INIT; }
             break;
         }
-        reload_context(d, dict_base);
+        reload_context<kV>(d, dict_base);
         run_lzma<kV>(d, wc, P, L, dict_base);
 
         // what the chunk did, as seen by every lane
@@ -432,7 +436,7 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     uint64_t outbits = (uint64_t)(uintptr_t)d.outp;
     LZ_BCAST32(code);
     LZ_BCAST64(outbits);
-    LZ_IF_LANE0 {
+    LZ_IF_LANE0_ONLY {
         res.status = status;
         res.err_site = site;
         res.bytes_out = (uint64_t)((uint8_t *)(uintptr_t)outbits - io.out);
