@@ -40,6 +40,9 @@
 #define LZ_FUNNEL_R(lo, hi, sh) __funnelshift_r((lo), (hi), (sh))   /* ((hi:lo) >> (sh & 31)) low word */
 #define LZ_SHR_CLAMP(x, sh) __funnelshift_rc((x), 0u, (sh))          /* x >> min(sh, 32) */
 // predicated global load: no branch, so lane 0's instruction stream stays straight-line
+// window byte -> 32-bit register, issued now, first touched when a literal needs it (anything
+// the compiler inserts in between -- a mask, a move -- would stall on the load right here)
+#define LZ_LD_WIN8(dst, p) asm volatile("ld.global.u8 %0, [%1];" : "=r"(dst) : "l"(p) : "memory")
 #define LZ_LD_IN32_IF(dst, p, cond)                                                     \
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}" \
                  : "+r"(dst) : "l"(p), "r"((uint32_t)(cond)))
@@ -55,6 +58,7 @@
 #define LZ_FUNNEL_R(lo, hi, sh) ((uint32_t)(((((uint64_t)(hi)) << 32 | (uint64_t)(lo)) >> ((sh) & 31))))
 #define LZ_SHR_CLAMP(x, sh) ((sh) >= 32 ? 0u : ((uint32_t)(x) >> (sh)))
 #define LZ_LD_IN32_IF(dst, p, cond) do { if (cond) (dst) = *(const uint32_t *)(p); } while (0)
+#define LZ_LD_WIN8(dst, p) ((dst) = *(const uint8_t *)(p))
 #define LZ_LIKELY(x) __builtin_expect(!!(x), 1)
 #define LZ_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #endif
@@ -101,6 +105,8 @@ struct Dec {
     uint32_t size_defined;          // state.unpackSizeDefined
     uint32_t lc, lp_mask, pos_mask;
     uint32_t prev_byte, mbyte;      // literal context: byte at -1 and at -(rep0+1)
+    uint32_t ctx_a, ctx_b;          // the same two bytes when a window copy has just loaded them ...
+    uint32_t ctx_pending;           // ... (then they supersede prev_byte / mbyte at the next literal)
     int32_t status, site;
 };
 
@@ -397,13 +403,18 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
                 if (d.end_is_size) LZ_FAIL(LZGPU_RESULT_ERROR, 46);
                 LZ_FAIL(LZGPU_OUTPUT_OVERFLOW, 0);
             }
-            uint16_t *pr = L + 0x300u * (((d.wpos & d.lp_mask) << d.lc) + (d.prev_byte >> (8 - d.lc)));  // :56-57
+            // context bytes: straight from the last window copy's loads if there was one (first use
+            // of those registers, so this is where a literal-after-match waits for the window)
+            const uint32_t prevb = d.ctx_pending ? d.ctx_a : d.prev_byte;
+            const uint32_t matchb = d.ctx_pending ? d.ctx_b : d.mbyte;
+            d.ctx_pending = 0;
+            uint16_t *pr = L + 0x300u * (((d.wpos & d.lp_mask) << d.lc) + (prevb >> (8 - d.lc)));  // :56-57
             // Plain and matched literals in one straight-line tree walk: `offs` is 0x100 while
             // the decoded prefix still equals the match byte's (matched mode, state >= 7,
             // :59-114) and drops to 0 at the first mismatch, after which the index is the
             // plain one (:127-166).  Index = offs + match_bit + sym = ((1 + matchBit) << 8) + sym.
             uint32_t offs = d.state >= 7 ? 0x100u : 0u;
-            uint32_t mb = d.mbyte;
+            uint32_t mb = matchb;
             uint32_t sym = 1;
 #pragma unroll
             for (int i = 0; i < 8; i++) {

@@ -118,6 +118,7 @@ LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8
             // dist > len (warp-uniform): no byte of the match depends on the match itself and
             // byte i simply comes from dst[i - dist]; otherwise the source repeats with period dist.
             const uint8_t *src = dst - dist;
+            const uint8_t *cprev, *cmatch;   // where the context bytes for a following literal live
             if (LZ_LIKELY(dist > len)) {
                 if (len <= 32) {
                     // deferred: load now, store at the next commit
@@ -131,13 +132,8 @@ LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8
                         for (uint32_t i = l; i < len; i += 32) dst[i] = src[i];
                     }
                 }
-                LZ_IF_LANE0 {
-                    // context for a literal / short rep that may follow: the last byte of the
-                    // match and the byte at -(rep0+1) after it.  Both predate the match.
-                    d.prev_byte = src[len - 1];
-                    d.mbyte = src[len];
-                    d.outp = dst + len;
-                }
+                cprev = src + (len - 1);
+                cmatch = src + len;
             } else {  // the match overlaps itself: period-dist replication (window.go:73-86)
                 if (len <= 32) {
                     LZ_FOR_LANES(l) {
@@ -150,11 +146,17 @@ LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8
                         for (uint32_t i = l; i < len; i += 32) dst[i] = src[src_index(i, dist)];
                     }
                 }
-                LZ_IF_LANE0 {
-                    d.prev_byte = src[src_index(len - 1, dist)];
-                    d.mbyte = src[src_index(len, dist)];
-                    d.outp = dst + len;
-                }
+                cprev = src + src_index(len - 1, dist);
+                cmatch = src + src_index(len, dist);
+            }
+            LZ_IF_LANE0 {
+                // context for a literal that may follow: the last byte of the match and the byte at
+                // -(rep0+1) after it.  Both predate the match.  One load site, results untouched
+                // until a literal asks for them.
+                LZ_LD_WIN8(d.ctx_a, cprev);
+                LZ_LD_WIN8(d.ctx_b, cmatch);
+                d.ctx_pending = 1;
+                d.outp = dst + len;
             }
         } else {  // OP_COPY_Q4: dist == bytes since dictionary start + 1; byte "-1" reads as 0
             LZ_IF_LANE0 {
@@ -165,6 +167,7 @@ LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8
                 d.prev_byte = dst[len - 1];
                 const uint8_t *m = dst + len - dist;
                 d.mbyte = m < dict_base ? (uint8_t)0 : *m;
+                d.ctx_pending = 0;
                 d.outp = dst + len;
             }
             LZ_SYNC();
@@ -184,6 +187,7 @@ LZ_DEV void reload_context(Dec &d, const uint8_t *dict_base) {
         const uint64_t hist = (uint64_t)(d.outp - dict_base);
         d.prev_byte = hist > 0 ? d.outp[-1] : 0;
         d.mbyte = ((uint64_t)d.rep0 + 1 <= hist) ? d.outp[-(int64_t)((uint64_t)d.rep0 + 1)] : 0;
+        d.ctx_pending = 0;
     }
 }
 
@@ -208,6 +212,8 @@ LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     d.full = 0;
     d.prev_byte = 0;
     d.mbyte = 0;
+    d.ctx_a = d.ctx_b = 0;
+    d.ctx_pending = 0;
     d.outp = io.out;
     d.size_defined = u.unpack_size != LZGPU_UNKNOWN_SIZE;   // state.go:135-151
     d.end_is_size = d.size_defined && u.unpack_size <= io.out_cap;
@@ -248,6 +254,8 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     d.full = 0;
     d.prev_byte = 0;
     d.mbyte = 0;
+    d.ctx_a = d.ctx_b = 0;
+    d.ctx_pending = 0;
     d.rep0 = d.rep1 = d.rep2 = d.rep3 = 0;
     d.state = 0;
     d.range = 0xFFFFFFFFu;
