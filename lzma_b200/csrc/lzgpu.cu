@@ -24,7 +24,7 @@
 using namespace lzgpu;
 
 #ifndef LZGPU_DEFAULT_VARIANT
-#define LZGPU_DEFAULT_VARIANT 3
+#define LZGPU_DEFAULT_VARIANT 11
 #endif
 
 // ------------------------------------------------------------------ kernel
@@ -76,6 +76,7 @@ static void launch_decode(int variant, unsigned grid, size_t smem, cudaStream_t 
         case 3: lzgpu_decode_kernel<kLitGlobal, 3><<<grid, 32, smem, st>>>(a); break;
         case 7: lzgpu_decode_kernel<kLitGlobal, 7><<<grid, 32, smem, st>>>(a); break;
         case 11: lzgpu_decode_kernel<kLitGlobal, 11><<<grid, 32, smem, st>>>(a); break;
+        case 15: lzgpu_decode_kernel<kLitGlobal, 15><<<grid, 32, smem, st>>>(a); break;
         default: lzgpu_decode_kernel<kLitGlobal, 0><<<grid, 32, smem, st>>>(a); break;
     }
 }

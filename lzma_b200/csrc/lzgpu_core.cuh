@@ -413,18 +413,33 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
             // the decoded prefix still equals the match byte's (matched mode, state >= 7,
             // :59-114) and drops to 0 at the first mismatch, after which the index is the
             // plain one (:127-166).  Index = offs + match_bit + sym = ((1 + matchBit) << 8) + sym.
-            uint32_t offs = d.state >= 7 ? 0x100u : 0u;
-            uint32_t mb = matchb;
             uint32_t sym = 1;
+            if ((kV & V_PREFETCH) && d.state < 7) {
+                // plain literal (:127-166): an 8-level bit tree; both children of a node share an
+                // aligned word, loaded before the bit that chooses between them is known
+                uint32_t pv = pr[1];
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                if ((i & 3) == 3) LZ_FILL();
-                mb += mb;
-                const uint32_t old = offs;
-                offs &= mb;                                      // match bit, if still in matched mode
-                LZ_BIT(pr + offs + old + sym, bit);
-                sym = (sym << 1) | bit;
-                offs ^= bit ? 0u : old;                          // stays set only while bit == match bit
+                for (int i = 0; i < 8; i++) {
+                    if ((i & 3) == 3) LZ_FILL();
+                    uint32_t pair = 0;
+                    if (i < 7) pair = LZ_PAIR(pr, sym);
+                    LZ_BIT_P(pr + sym, pv, bit);
+                    sym = (sym << 1) | bit;
+                    pv = LZ_PICK(pair, bit);
+                }
+            } else {
+                uint32_t offs = d.state >= 7 ? 0x100u : 0u;
+                uint32_t mb = matchb;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if ((i & 3) == 3) LZ_FILL();
+                    mb += mb;
+                    const uint32_t old = offs;
+                    offs &= mb;                                      // match bit, if still in matched mode
+                    LZ_BIT(pr + offs + old + sym, bit);
+                    sym = (sym << 1) | bit;
+                    offs ^= bit ? 0u : old;                          // stays set only while bit == match bit
+                }
             }
             if (LZ_UNLIKELY(LZ_EXHAUSTED())) goto input_eof;
             sym &= 0xFF;
