@@ -90,7 +90,6 @@ enum : uint32_t { OP_COPY = 0, OP_COPY_Q4 = 1, OP_DONE = 2, OP_SWITCH = 3 };
 // Lane 0's decoder registers.
 struct Dec {
     uint32_t range, code;
-    uint32_t r11;                   // range >> 11, kept one step ahead (off the serial chain)
     uint32_t inb_hi, inb_lo;        // 64-bit input lookahead, next byte in the top 8 bits of inb_hi
     uint32_t inbits;                // bits in the lookahead (real bytes first, then phantom zeros)
     uint32_t phantom;               // zero BITS appended after the real input ran out
@@ -215,7 +214,6 @@ LZ_HD void set_fast_limits(Dec &d) {
 // 0 ok, 1 first byte != 0, -1 fewer than 5 bytes.
 LZ_HD int rc_init(Dec &d) {
     d.range = 0xFFFFFFFFu;
-    d.r11 = 0xFFFFFFFFu >> 11;
     d.code = 0;
     d.inb_hi = d.inb_lo = 0;
     d.inbits = 0;
@@ -234,11 +232,7 @@ LZ_HD int rc_init(Dec &d) {
 // no branch, so no convergence barrier and no fetch bubble in lane 0's instruction stream.
 #define LZ_NORM()                                                                   \
     do {                                                                            \
-        const bool n_ = d.range < kTop;                                             \
-        const uint32_t sh_ = n_ ? 8u : 0u;                                          \
-        /* next step's range >> 11 from both candidates at once: two cycles of the */ \
-        /* serial range -> bound -> compare -> range chain saved per bit           */ \
-        d.r11 = n_ ? d.range >> 3 : d.range >> 11;                                  \
+        const uint32_t sh_ = d.range < kTop ? 8u : 0u;                              \
         d.range <<= sh_;                                                            \
         d.code = LZ_FUNNEL_L(d.inb_hi, d.code, sh_);                                \
         d.inb_hi = LZ_FUNNEL_L(d.inb_lo, d.inb_hi, sh_);                            \
@@ -253,7 +247,7 @@ LZ_HD int rc_init(Dec &d) {
     do {                                                                            \
         uint16_t *pp_ = (PP);                                                       \
         const uint32_t p_ = *pp_;                                                   \
-        const uint32_t bound_ = d.r11 * p_;                                         \
+        const uint32_t bound_ = (d.range >> 11) * p_;                               \
         const bool one_ = d.code >= bound_;                                         \
         d.range = one_ ? d.range - bound_ : bound_;                                 \
         d.code = one_ ? d.code - bound_ : d.code;                                   \
@@ -266,7 +260,7 @@ LZ_HD int rc_init(Dec &d) {
 #define LZ_BIT_P(PP, PVAL, BIT)                                                     \
     do {                                                                            \
         const uint32_t p_ = (PVAL);                                                 \
-        const uint32_t bound_ = d.r11 * p_;                                         \
+        const uint32_t bound_ = (d.range >> 11) * p_;                               \
         const bool one_ = d.code >= bound_;                                         \
         d.range = one_ ? d.range - bound_ : bound_;                                 \
         d.code = one_ ? d.code - bound_ : d.code;                                   \
@@ -508,7 +502,6 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
                             g = 8;
                             if (n == 0) break;
                         }
-                        d.r11 = d.range >> 11;
                     } else {
                         for (uint32_t n = nd - 4; n > 0; n--) {   // DecodeDirectBits, :549-576
                             if ((n & 3) == 0) LZ_FILL();

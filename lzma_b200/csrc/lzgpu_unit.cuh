@@ -259,7 +259,6 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     d.rep0 = d.rep1 = d.rep2 = d.rep3 = 0;
     d.state = 0;
     d.range = 0xFFFFFFFFu;
-    d.r11 = 0xFFFFFFFFu >> 11;
     d.code = 0;
     d.inb_hi = d.inb_lo = 0;
     d.inbits = 0;
