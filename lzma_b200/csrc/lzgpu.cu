@@ -71,12 +71,8 @@ static int decoder_variant() {
 template <bool kLitGlobal>
 static void launch_decode(int variant, unsigned grid, size_t smem, cudaStream_t st, const KArgs &a) {
     switch (variant) {
-        case 1: lzgpu_decode_kernel<kLitGlobal, 1><<<grid, 32, smem, st>>>(a); break;
-        case 2: lzgpu_decode_kernel<kLitGlobal, 2><<<grid, 32, smem, st>>>(a); break;
         case 3: lzgpu_decode_kernel<kLitGlobal, 3><<<grid, 32, smem, st>>>(a); break;
-        case 7: lzgpu_decode_kernel<kLitGlobal, 7><<<grid, 32, smem, st>>>(a); break;
         case 11: lzgpu_decode_kernel<kLitGlobal, 11><<<grid, 32, smem, st>>>(a); break;
-        case 15: lzgpu_decode_kernel<kLitGlobal, 15><<<grid, 32, smem, st>>>(a); break;
         default: lzgpu_decode_kernel<kLitGlobal, 0><<<grid, 32, smem, st>>>(a); break;
     }
 }

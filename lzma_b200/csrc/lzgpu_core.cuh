@@ -158,12 +158,10 @@ LZ_HD void rc_fill(Dec &d) {
 //   V_FAST         allow the fast decoder at all
 //   V_DIRECT_GROUP equiprobable bits in runs between two normalisations (their position is
 //                  known from the range's leading zeros) instead of a full step per bit
-//   V_PREFETCH     bit trees load BOTH children of the current node (one aligned 32-bit LDS)
-//                  before the bit is known, so the shared-memory latency leaves the serial chain
 //   V_UNIFORM      all 32 lanes run the serial decoder redundantly on identical data instead of
 //                  lane 0 alone: same issue cost (SIMT), but no divergence entry/exit and no
 //                  shuffles per match; same-address shared/global accesses are broadcasts
-enum : int { V_FAST = 1, V_DIRECT_GROUP = 2, V_PREFETCH = 4, V_UNIFORM = 8 };
+enum : int { V_FAST = 1, V_DIRECT_GROUP = 2, V_UNIFORM = 8 };
 constexpr uint32_t kFastInMargin = 64;    // >= 48 bit steps of one symbol + one word loaded ahead + slack
 constexpr uint32_t kFastOutMargin = 274;  // longest match is 273
 
@@ -256,19 +254,6 @@ LZ_HD int rc_init(Dec &d) {
         LZ_NORM();                                                                  \
     } while (0)
 
-// The same with the probability value already in a register (prefetched); PP is where to store it.
-#define LZ_BIT_P(PP, PVAL, BIT)                                                     \
-    do {                                                                            \
-        const uint32_t p_ = (PVAL);                                                 \
-        const uint32_t bound_ = (d.range >> 11) * p_;                               \
-        const bool one_ = d.code >= bound_;                                         \
-        d.range = one_ ? d.range - bound_ : bound_;                                 \
-        d.code = one_ ? d.code - bound_ : d.code;                                   \
-        *(PP) = (uint16_t)(p_ + (uint32_t)((int32_t)((one_ ? 31u : 2048u) - p_) >> 5)); \
-        (BIT) = one_ ? 1u : 0u;                                                     \
-        LZ_NORM();                                                                  \
-    } while (0)
-
 // One equiprobable bit (DecodeDirectBits, range_decoder.go:100-134 / decompress.go:549-576)
 #define LZ_DIRECT(RES)                                                              \
     do {                                                                            \
@@ -279,33 +264,16 @@ LZ_HD int rc_init(Dec &d) {
         LZ_NORM();                                                                  \
     } while (0)
 
-// Children of node m are entries 2m and 2m+1: one aligned 32-bit load when the table base is
-// 4-byte aligned (all P_* bases and sub-table strides are even).
-#define LZ_PAIR(TP, M) (*reinterpret_cast<const uint32_t *>((TP) + 2u * (M)))
-#define LZ_PICK(PAIR, BIT) ((BIT) ? ((PAIR) >> 16) : ((PAIR) & 0xFFFFu))
-
 // MSB-first bit tree (BitTreeDecode, bit_tree_decoder.go:26-76), NBITS constant, unrolled.
 // FILL_AT: a fill is issued before bit i whenever (i & 3) == FILL_AT (keeps <= 4 steps per fill).
 #define LZ_TREE(PROBS, NBITS, OUT, FILL_AT)                                         \
     do {                                                                            \
         uint16_t *tp_ = (PROBS);                                                    \
         uint32_t m_ = 1, b_;                                                        \
-        if (kV & V_PREFETCH) {                                                      \
-            uint32_t pv_ = tp_[1];                                                  \
-            _Pragma("unroll") for (int i_ = 0; i_ < (NBITS); i_++) {                \
-                if ((i_ & 3) == (FILL_AT)) LZ_FILL();                               \
-                uint32_t pair_ = 0;                                                 \
-                if (i_ + 1 < (NBITS)) pair_ = LZ_PAIR(tp_, m_);                     \
-                LZ_BIT_P(tp_ + m_, pv_, b_);                                        \
-                m_ = (m_ << 1) | b_;                                                \
-                pv_ = LZ_PICK(pair_, b_);                                           \
-            }                                                                       \
-        } else {                                                                    \
-            _Pragma("unroll") for (int i_ = 0; i_ < (NBITS); i_++) {                \
-                if ((i_ & 3) == (FILL_AT)) LZ_FILL();                               \
-                LZ_BIT(tp_ + m_, b_);                                               \
-                m_ = (m_ << 1) | b_;                                                \
-            }                                                                       \
+        _Pragma("unroll") for (int i_ = 0; i_ < (NBITS); i_++) {                    \
+            if ((i_ & 3) == (FILL_AT)) LZ_FILL();                                   \
+            LZ_BIT(tp_ + m_, b_);                                                   \
+            m_ = (m_ << 1) | b_;                                                    \
         }                                                                           \
         (OUT) = m_ - (1u << (NBITS));                                               \
     } while (0)
@@ -316,27 +284,12 @@ LZ_HD int rc_init(Dec &d) {
         uint16_t *tp_ = (PROBS);                                                    \
         uint32_t m_ = 1, b_, s_ = 0;                                                \
         const uint32_t nb_ = (NBITS);                                               \
-        if (kV & V_PREFETCH) {                                                      \
-            uint32_t pv_ = tp_[1];                                                  \
-            _Pragma("unroll") for (uint32_t i_ = 0; i_ < (MAXBITS); i_++) {         \
-                if (i_ < nb_) {                                                     \
-                    if (i_ == 4) LZ_FILL();                                         \
-                    uint32_t pair_ = 0;                                             \
-                    if (i_ + 1 < nb_) pair_ = LZ_PAIR(tp_, m_);               \
-                    LZ_BIT_P(tp_ + m_, pv_, b_);                                    \
-                    m_ = (m_ << 1) | b_;                                            \
-                    s_ |= b_ << i_;                                                 \
-                    pv_ = LZ_PICK(pair_, b_);                                       \
-                }                                                                   \
-            }                                                                       \
-        } else {                                                                    \
-            _Pragma("unroll") for (uint32_t i_ = 0; i_ < (MAXBITS); i_++) {         \
-                if (i_ < nb_) {                                                     \
-                    if (i_ == 4) LZ_FILL();                                         \
-                    LZ_BIT(tp_ + m_, b_);                                           \
-                    m_ = (m_ << 1) | b_;                                            \
-                    s_ |= b_ << i_;                                                 \
-                }                                                                   \
+        _Pragma("unroll") for (uint32_t i_ = 0; i_ < (MAXBITS); i_++) {             \
+            if (i_ < nb_) {                                                         \
+                if (i_ == 4) LZ_FILL();                                             \
+                LZ_BIT(tp_ + m_, b_);                                               \
+                m_ = (m_ << 1) | b_;                                                \
+                s_ |= b_ << i_;                                                     \
             }                                                                       \
         }                                                                           \
         (OUT) = s_;                                                                 \
@@ -414,32 +367,17 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
             // :59-114) and drops to 0 at the first mismatch, after which the index is the
             // plain one (:127-166).  Index = offs + match_bit + sym = ((1 + matchBit) << 8) + sym.
             uint32_t sym = 1;
-            if ((kV & V_PREFETCH) && d.state < 7) {
-                // plain literal (:127-166): an 8-level bit tree; both children of a node share an
-                // aligned word, loaded before the bit that chooses between them is known
-                uint32_t pv = pr[1];
+            uint32_t offs = d.state >= 7 ? 0x100u : 0u;
+            uint32_t mb = matchb;
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if ((i & 3) == 3) LZ_FILL();
-                    uint32_t pair = 0;
-                    if (i < 7) pair = LZ_PAIR(pr, sym);
-                    LZ_BIT_P(pr + sym, pv, bit);
-                    sym = (sym << 1) | bit;
-                    pv = LZ_PICK(pair, bit);
-                }
-            } else {
-                uint32_t offs = d.state >= 7 ? 0x100u : 0u;
-                uint32_t mb = matchb;
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if ((i & 3) == 3) LZ_FILL();
-                    mb += mb;
-                    const uint32_t old = offs;
-                    offs &= mb;                                      // match bit, if still in matched mode
-                    LZ_BIT(pr + offs + old + sym, bit);
-                    sym = (sym << 1) | bit;
-                    offs ^= bit ? 0u : old;                          // stays set only while bit == match bit
-                }
+            for (int i = 0; i < 8; i++) {
+                if ((i & 3) == 3) LZ_FILL();
+                mb += mb;
+                const uint32_t old = offs;
+                offs &= mb;                                      // match bit, if still in matched mode
+                LZ_BIT(pr + offs + old + sym, bit);
+                sym = (sym << 1) | bit;
+                offs ^= bit ? 0u : old;                          // stays set only while bit == match bit
             }
             if (LZ_UNLIKELY(LZ_EXHAUSTED())) goto input_eof;
             sym &= 0xFF;
@@ -468,8 +406,7 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
                 uint32_t dist = (2 | (slot & 1)) << nd, v;
                 LZ_FILL();
                 if (slot < 14) {                                  // :494-546
-                    // own sub-table layout: slot s starts at dist - 4 (always even, so that a node's
-                    // two children share an aligned word); the reference's is dist - slot (:496)
+                    // own sub-table layout: slot s starts at dist - 4; the reference's is dist - slot (:496)
                     LZ_TREE_REV(P + P_POS_DEC + dist - 4, nd, v, 5);
                     dist += v;
                 } else {                                          // :548-628

@@ -44,12 +44,8 @@ extern "C" int emu_decode_batch(const lzgpu_unit *units, int64_t n, const uint8_
         r.status = LZGPU_NOT_RUN;
         uint16_t *P = probs.data(), *L = probs.data() + P_LIT;
         switch (variant) {
-            case 1: run_one<1>(u, io, P, L, bits, r); break;
-            case 2: run_one<2>(u, io, P, L, bits, r); break;
             case 3: run_one<3>(u, io, P, L, bits, r); break;
-            case 7: run_one<7>(u, io, P, L, bits, r); break;
             case 11: run_one<11>(u, io, P, L, bits, r); break;
-            case 15: run_one<15>(u, io, P, L, bits, r); break;
             default: run_one<0>(u, io, P, L, bits, r); break;
         }
         if (alone) r.bytes_in += 13;
