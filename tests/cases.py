@@ -107,3 +107,38 @@ def lzma2_cases(seed: int = 2):
     cases.append(("trunc_no_terminator", s[:-1], 1 << 20, total))
     cases.append(("trunc_header_2", s[:2], 1 << 20, total))
     return cases
+
+
+def encoder_cases(seed: int = 3, heavy: bool = True):
+    """Streams only our test encoder can write (tests/enc): every prop byte the reference accepts
+    (lc 0-8, lp 0-4, pb 0-4 -- liblzma stops at lc+lp = 4), size-only / EOS-only / both, odd
+    dictionary sizes (Q3: wrapped-position contexts), a match at position 0 (Q4), long runs."""
+    import encoder as E
+    rng = random.Random(seed)
+    d = K.mixed_block(5, 9_000) + K.text_block(6, 6_000)
+    cases = []
+    for lc, lp, pb in itertools.product(range(9), range(5), range(5)):
+        if not heavy and (lc * 7 + lp * 3 + pb) % 5:
+            continue
+        fl = rng.choice([E.EOS, E.SIZE, E.EOS | E.SIZE])
+        cases.append((f"enc_lc{lc}_lp{lp}_pb{pb}_f{fl}", E.encode(d, lc, lp, pb, 1 << 16, fl), len(d) + 3))
+    for ds in (4096, 4097, 4100, 5000, 7777, 65_537):
+        dd = K.mixed_block(9 + ds, 60_000)
+        cases.append((f"enc_dict_{ds}", E.encode(dd, 3, 1, 2, ds, E.EOS), len(dd)))
+        cases.append((f"enc_dict_{ds}_pb4_lp4", E.encode(dd, 0, 4, 4, ds, E.SIZE), len(dd)))
+    z = bytes(300) + K.text_block(1, 2_000)
+    cases.append(("enc_q4_match_at_position_0", E.encode(z, 3, 0, 2, 1 << 16, E.EOS | E.Q4_START), len(z)))
+    z2 = bytes(3000)
+    cases.append(("enc_q4_all_zero", E.encode(z2, 2, 2, 0, 4096, E.SIZE | E.Q4_START), len(z2)))
+    runs = b"".join(bytes([i]) * (280 + 31 * i) for i in range(30)) + b"abcd" * 4000 + bytes(50_000)
+    cases.append(("enc_runs", E.encode(runs, 3, 0, 2, 1 << 20, E.EOS | E.SIZE), len(runs)))
+    big = K.text_block(77, 400_000)
+    cases.append(("enc_text_400k_dict64k", E.encode(big, 3, 0, 2, 1 << 16, E.EOS), len(big)))
+    s = E.encode(d, 8, 4, 4, 1 << 16, E.EOS | E.SIZE)
+    for r in range(4 if heavy else 1):   # corrupt streams with huge literal tables
+        b = bytearray(s)
+        i = rng.randrange(13, len(b))
+        b[i] ^= 1 << rng.randrange(8)
+        cases.append((f"enc_flip_lc8lp4_{r}", bytes(b), len(d) + 50_000))
+        cases.append((f"enc_trunc_lc8lp4_{r}", s[:rng.randrange(14, len(s))], len(d) + 50_000))
+    return cases

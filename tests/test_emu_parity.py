@@ -29,3 +29,11 @@ def test_lzma2_cases(ctx):
     for name, s, dict_size, cap in cases.lzma2_cases():
         st, site, data = B.decode_lzma2_stream(ctx, s, dict_size)
         same_outcome(O.lzma2(s, dict_size, cap + (1 << 20)), st, site, data, name, strict_site=False)
+
+
+def test_encoder_cases(ctx):
+    """Props beyond liblzma's limits, odd dictionaries (Q3), match at position 0 (Q4)."""
+    cs = cases.encoder_cases(heavy=False)
+    got = B.decode_alone_streams(ctx, [c[1] for c in cs], [c[2] for c in cs])
+    for (name, s, cap), g in zip(cs, got):
+        same_outcome(O.lzma_alone(s, cap), g.status, g.err_site, g.data, name)

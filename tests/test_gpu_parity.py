@@ -49,6 +49,15 @@ def test_alone_cases(ctx):
         same_outcome(O.lzma_alone(s, cap), g.status, g.err_site, g.data, name)
 
 
+def test_encoder_cases(ctx):
+    """All 225 prop bytes the reference accepts (lc+lp up to 12: literal tables in HBM), size-only
+    streams, odd dictionaries (Q3), a match at position 0 (Q4), corrupt streams with large tables."""
+    cs = cases.encoder_cases(heavy=True)
+    got = B.decode_alone_streams(ctx, [c[1] for c in cs], [c[2] for c in cs])
+    for (name, s, cap), g in zip(cs, got):
+        same_outcome(O.lzma_alone(s, cap), g.status, g.err_site, g.data, name)
+
+
 def test_lzma2_cases(ctx):
     for name, s, dict_size, cap in cases.lzma2_cases():
         st, site, data = B.decode_lzma2_stream(ctx, s, dict_size)
@@ -123,3 +132,96 @@ def test_tuning_variants_agree(variant, monkeypatch):
         for name, s, dict_size, cap in cases.lzma2_cases()[:6]:
             st, site, data = B.decode_lzma2_stream(c, s, dict_size)
             same_outcome(O.lzma2(s, dict_size, cap + (1 << 20)), st, site, data, f"v{variant}:{name}", strict_site=False)
+
+
+def test_lzma2_stream_many_units(ctx):
+    """BASELINE config 3 at reduced size: one raw LZMA2 stream with a dictionary reset every 1 MiB;
+    the host scanner cuts it into units that decode in parallel.  Compared with the plaintext."""
+    n_blocks = 48
+    blocks = [K.text_block(500 + i, 1 << 20) for i in range(4)]
+    parts = [K.compress_raw_lzma2(b) for b in blocks]
+    seq = [i % 4 for i in range(n_blocks)]
+    stream = b"".join(parts[i][:-1] for i in seq[:-1]) + parts[seq[-1]]
+    units, total, sst = B.scan_lzma2(stream, 8 << 20)
+    assert len(units) == n_blocks and total == n_blocks << 20 and sst == L.OK
+    st, site, data = B.decode_lzma2_stream(ctx, stream, 8 << 20)
+    assert st == L.OK and len(data) == total
+    for k, i in enumerate(seq):
+        assert zlib.crc32(data[k << 20:(k + 1) << 20]) == zlib.crc32(blocks[i]), f"block {k}"
+
+
+def test_mixed_kinds_one_batch(ctx):
+    """BASELINE config 4: .lzma units, headerless LZMA1 units, LZMA2 groups (with uncompressed chunks),
+    incompressible data and corrupt streams in ONE lzgpu_decode_batch call; a bad unit must not poison
+    its neighbours."""
+    plain = [K.text_block(1, 90_000), K.random_block(2, 50_000), K.mixed_block(3, 120_000)]
+    alone = [K.compress_alone(p, lc, lp, pb) for p, (lc, lp, pb) in zip(plain, [(3, 0, 2), (0, 4, 0), (4, 0, 4)])]
+    l2_data = [K.text_block(4, 300_000), K.random_block(5, 100_000), K.text_block(6, 150_000)]
+    l2 = K.lzma2_with_resets(l2_data, dict_size=1 << 20)
+    l2_units, l2_total, _ = B.scan_lzma2(l2, 1 << 20)
+    bad = [cases.asset("bad_corrupted.lzma"), cases.asset("bad_incorrect_size.lzma"), alone[0][:5000]]
+    blobs, units, off, out_off = [], [], 0, 0
+
+    def add(u, blob, cap):
+        nonlocal off, out_off
+        u.in_off += off
+        u.out_off += out_off
+        units.append(u)
+
+    layout = []
+    for s in alone + bad:
+        st, u = B.parse_alone_header(s)
+        u.kind = L.KIND_LZMA1_ALONE
+        u.in_off, u.in_len, u.out_off, u.out_cap = off, len(s), out_off, 200_000
+        units.append(u)
+        blobs.append(s)
+        layout.append(("alone", s, 200_000))
+        off += (len(s) + 15) & ~15
+        blobs.append(b"\0" * (off - sum(map(len, blobs))))
+        out_off += 200_016
+    raw = L.Unit()   # sevenzip-style headerless unit: props from the caller
+    s = alone[2]
+    raw.kind, raw.lc, raw.lp, raw.pb, raw.dict_size, raw.unpack_size = L.KIND_LZMA1_RAW, 4, 0, 4, 8 << 20, len(plain[2])
+    raw.in_off, raw.in_len, raw.out_off, raw.out_cap = off, len(s) - 13, out_off, len(plain[2])
+    units.append(raw)
+    blobs.append(s[13:])
+    off += (len(s) - 13 + 15) & ~15
+    blobs.append(b"\0" * (off - sum(map(len, blobs))))
+    out_off += (len(plain[2]) + 15) & ~15
+    l2_base_in, l2_base_out = off, out_off
+    for u in l2_units:
+        u.in_off += l2_base_in
+        u.out_off += l2_base_out
+        units.append(u)
+    blobs.append(l2)
+    in_buf = np.frombuffer(b"".join(blobs) + bytes(16), dtype=np.uint8)
+    out_buf = np.zeros(out_off + l2_total + 16, dtype=np.uint8)
+    res, st = ctx.decode_batch(units, in_buf, out_buf)
+    k = 0
+    for kind, s, cap in layout:
+        want = O.lzma_alone(s, cap)
+        r, u = res[k], units[k]
+        same_outcome(want, r.status, r.err_site, out_buf[u.out_off:u.out_off + r.bytes_out].tobytes(), f"unit{k}")
+        k += 1
+    r, u = res[k], units[k]
+    assert r.status == L.OK and out_buf[u.out_off:u.out_off + r.bytes_out].tobytes() == plain[2]
+    k += 1
+    got = b""
+    for u in l2_units:
+        assert res[k].status == L.OK
+        got += out_buf[u.out_off:u.out_off + res[k].bytes_out].tobytes()
+        k += 1
+    assert got == b"".join(l2_data)
+    assert st.launches >= 3      # three literal-table classes (lc+lp = 3, 4) and both kinds ran
+
+
+def test_batch_over_all_visible_gpus():
+    """lzgpu_decode_batch sharding over every GPU the box has (1 on the default test box)."""
+    with B.Context() as c:
+        plains = [K.text_block(900 + i, 60_000 + 5_000 * (i % 5)) for i in range(40)]
+        got = B.decode_alone_streams(c, [K.compress_alone(p, preset=1) for p in plains])
+        devs = set()
+        for p, g in zip(plains, got):
+            assert g.status == L.OK and g.data == p
+            devs.add(g.device)
+        assert len(devs) == c.n_devices or c.n_devices > len(plains)
