@@ -44,7 +44,7 @@
 // the compiler inserts in between -- a mask, a move -- would stall on the load right here)
 #define LZ_LD_WIN8(dst, p) asm volatile("ld.global.u8 %0, [%1];" : "=r"(dst) : "l"(p) : "memory")
 #define LZ_LD_IN32_IF(dst, p, cond)                                                     \
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}" \
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}" \
                  : "+r"(dst) : "l"(p), "r"((uint32_t)(cond)))
 #define LZ_LIKELY(x) __builtin_expect(!!(x), 1)
 #define LZ_UNLIKELY(x) __builtin_expect(!!(x), 0)
@@ -362,32 +362,22 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
             const uint32_t matchb = d.ctx_pending ? d.ctx_b : d.mbyte;
             d.ctx_pending = 0;
             uint16_t *pr = L + 0x300u * (((d.wpos & d.lp_mask) << d.lc) + (prevb >> (8 - d.lc)));  // :56-57
+            // Plain and matched literals in one straight-line tree walk: `offs` is 0x100 while
+            // the decoded prefix still equals the match byte's (matched mode, state >= 7,
+            // :59-114) and drops to 0 at the first mismatch, after which the index is the
+            // plain one (:127-166).  Index = offs + match_bit + sym = ((1 + matchBit) << 8) + sym.
             uint32_t sym = 1;
-            if (d.state < 7) {
-                // plain literal (:127-166): an 8-level bit tree over pr[1..255]
+            uint32_t offs = d.state >= 7 ? 0x100u : 0u;
+            uint32_t mb = matchb;
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if ((i & 3) == 3) LZ_FILL();
-                    LZ_BIT(pr + sym, bit);
-                    sym = (sym << 1) | bit;
-                }
-            } else {
-                // matched literal (:59-114) falling back to the plain table at the first mismatch, as
-                // one straight-line walk: `offs` is 0x100 while the decoded prefix still equals the
-                // match byte's and drops to 0 afterwards; index = offs + match_bit + sym
-                // = ((1 + matchBit) << 8) + sym in matched mode, sym in plain mode.
-                uint32_t offs = 0x100u;
-                uint32_t mb = matchb;
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if ((i & 3) == 3) LZ_FILL();
-                    mb += mb;
-                    const uint32_t old = offs;
-                    offs &= mb;                                      // match bit, if still in matched mode
-                    LZ_BIT(pr + offs + old + sym, bit);
-                    sym = (sym << 1) | bit;
-                    offs ^= bit ? 0u : old;                          // stays set only while bit == match bit
-                }
+            for (int i = 0; i < 8; i++) {
+                if ((i & 3) == 3) LZ_FILL();
+                mb += mb;
+                const uint32_t old = offs;
+                offs &= mb;                                      // match bit, if still in matched mode
+                LZ_BIT(pr + offs + old + sym, bit);
+                sym = (sym << 1) | bit;
+                offs ^= bit ? 0u : old;                          // stays set only while bit == match bit
             }
             if (LZ_UNLIKELY(LZ_EXHAUSTED())) goto input_eof;
             sym &= 0xFF;
