@@ -309,7 +309,7 @@ LZ_HD int rc_init(Dec &d) {
         } else {                                                                    \
             LZ_BIT(lp_ + LEN_CHOICE2, lb_);                                         \
             LZ_FILL();                                                              \
-            if (lb_ == 0) {                                                         \
+            if (LZ_LIKELY(lb_ == 0)) {                                              \
                 LZ_TREE(lp_ + LEN_MID + ((POS_STATE) << 3), 3, lv_, 7);             \
                 (LEN) = 8 + lv_; (WHICH) = 1;                                       \
             } else {                                                                \
@@ -399,13 +399,13 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
             const uint32_t len_state = len > 3 ? 3 : len;         // :434-437
             uint32_t slot;
             LZ_TREE(P + P_POS_SLOT + (len_state << 6), 6, slot, 0);  // :441-486
-            if (slot < 4) {
+            if (LZ_UNLIKELY(slot < 4)) {
                 d.rep0 = slot;                                    // :488-489
             } else {
                 const uint32_t nd = (slot >> 1) - 1;
                 uint32_t dist = (2 | (slot & 1)) << nd, v;
                 LZ_FILL();
-                if (slot < 14) {                                  // :494-546
+                if (LZ_UNLIKELY(slot < 14)) {                     // :494-546
                     // own sub-table layout: slot s starts at dist - 4; the reference's is dist - slot (:496)
                     LZ_TREE_REV(P + P_POS_DEC + dist - 4, nd, v, 5);
                     dist += v;
