@@ -112,7 +112,11 @@ struct Dec {
 
 // Input is consumed through a 64-bit lookahead register so that the per-bit
 // normalisation is branch-free; LZ_FILL() tops it up to >= 4 bytes and is placed so
-// that at most 4 bit steps run between two fills.  When the real input runs out the
+// that at most 5 adaptive bit steps run between two fills.  Five steps cannot consume
+// more than 4 bytes: a step shrinks the range by at most 31/2048 (probabilities stay
+// within [31, 2017]), i.e. log2(range) drops by < 6.05, each normalisation adds 8 and
+// log2(range) lives in [24, 32) between steps, so k steps normalise at most
+// floor((8 + 6.05 k) / 8) times: 4 for k = 5.  When the real input runs out the
 // lookahead is padded with zero bytes that are counted in d.phantom: the reference
 // stops (io.EOF from ReadByte, decompress.go:35-38) exactly when the decoder would
 // consume the first of them, i.e. when d.phantom > d.inbits, which is tested before
@@ -166,20 +170,33 @@ constexpr uint32_t kFastInMargin = 64;    // >= 48 bit steps of one symbol + one
 constexpr uint32_t kFastOutMargin = 274;  // longest match is 273
 
 #define LZ_FILL32() do { if (LZ_UNLIKELY(d.inbits < 32)) rc_fill(d); } while (0)
-#define LZ_FILL()                                                                   \
+#if defined(__CUDA_ARCH__)
+// fast-mode top-up, all predicated: append the word in hand below the valid bits, count it, fetch
+// the next word, advance.  lo is 0 whenever inbits < 32, so lo = (w:0) >> inbits (low word).
+#define LZ_FILL_FAST()                                                              \
+    asm("{\n\t.reg .pred q;\n\t.reg .b32 w, t;\n\t"                               \
+        "setp.lt.u32 q, %2, 32;\n\t"                                                \
+        "prmt.b32 w, %3, 0, 0x0123;\n\t"                                            \
+        "shr.u32 t, w, %2;\n\t"            /* 0 when inbits >= 32 */               \
+        "or.b32 %0, %0, t;\n\t"                                                     \
+        "@q shf.r.wrap.b32 %1, 0, w, %2;\n\t"                                       \
+        "@q add.u32 %2, %2, 32;\n\t"                                                \
+        "@q ld.global.nc.u32 %3, [%4];\n\t"                                         \
+        "@q add.u64 %4, %4, 4;\n\t}"                                                \
+        : "+r"(d.inb_hi), "+r"(d.inb_lo), "+r"(d.inbits), "+r"(d.nextw), "+l"(d.ip))
+#else
+#define LZ_FILL_FAST()                                                              \
     do {                                                                            \
-        if (kFast) {                                                                \
-            const bool f_ = d.inbits < 32;      /* then inb_lo == 0 */             \
-            const uint32_t w_ = LZ_BSWAP32(d.nextw);                                \
-            d.inb_hi |= LZ_SHR_CLAMP(w_, d.inbits);   /* adds nothing when inbits >= 32 */ \
-            d.inb_lo = f_ ? LZ_FUNNEL_R(0u, w_, d.inbits) : d.inb_lo;               \
-            d.inbits += f_ ? 32u : 0u;                                              \
-            LZ_LD_IN32_IF(d.nextw, d.ip, f_);                                       \
-            d.ip += f_ ? 4 : 0;                                                     \
-        } else {                                                                    \
-            LZ_FILL32();                                                            \
-        }                                                                           \
+        const bool f_ = d.inbits < 32;      /* then inb_lo == 0 */                 \
+        const uint32_t w_ = LZ_BSWAP32(d.nextw);                                    \
+        d.inb_hi |= LZ_SHR_CLAMP(w_, d.inbits);   /* adds nothing when inbits >= 32 */ \
+        d.inb_lo = f_ ? LZ_FUNNEL_R(0u, w_, d.inbits) : d.inb_lo;                   \
+        d.inbits += f_ ? 32u : 0u;                                                  \
+        LZ_LD_IN32_IF(d.nextw, d.ip, f_);                                           \
+        d.ip += f_ ? 4 : 0;                                                         \
     } while (0)
+#endif
+#define LZ_FILL() do { if (kFast) LZ_FILL_FAST(); else LZ_FILL32(); } while (0)
 #define LZ_SHIFT8()                                                                 \
     do {                                                                            \
         d.range <<= 8;                                                              \
@@ -265,13 +282,13 @@ LZ_HD int rc_init(Dec &d) {
     } while (0)
 
 // MSB-first bit tree (BitTreeDecode, bit_tree_decoder.go:26-76), NBITS constant, unrolled.
-// FILL_AT: a fill is issued before bit i whenever (i & 3) == FILL_AT (keeps <= 4 steps per fill).
-#define LZ_TREE(PROBS, NBITS, OUT, FILL_AT)                                         \
+// FILL_MASK: bit i set = top the lookahead up before tree bit i.
+#define LZ_TREE(PROBS, NBITS, OUT, FILL_MASK)                                         \
     do {                                                                            \
         uint16_t *tp_ = (PROBS);                                                    \
         uint32_t m_ = 1, b_;                                                        \
         _Pragma("unroll") for (int i_ = 0; i_ < (NBITS); i_++) {                    \
-            if ((i_ & 3) == (FILL_AT)) LZ_FILL();                                   \
+            if (((FILL_MASK) >> i_) & 1) LZ_FILL();                                 \
             LZ_BIT(tp_ + m_, b_);                                                   \
             m_ = (m_ << 1) | b_;                                                    \
         }                                                                           \
@@ -296,24 +313,23 @@ LZ_HD int rc_init(Dec &d) {
     } while (0)
 
 // lenDecoder.Decode (len_decoder.go:34-60); WHICH = 0 low, 1 mid, 2 high.
-// Entered with >= 2 lookahead bytes to spare; leaves by itself filled as needed.
+// Entered right after a fill: choice, choice2 and a 3-bit tree are 5 steps; the 8-bit high tree
+// tops up again before its bits 3 and 7 (0x88).
 #define LZ_LEN(LP, POS_STATE, LEN, WHICH)                                           \
     do {                                                                            \
         uint16_t *lp_ = (LP);                                                       \
         uint32_t lb_, lv_;                                                          \
         LZ_BIT(lp_ + LEN_CHOICE, lb_);                                              \
         if (lb_ == 0) {                                                             \
-            LZ_FILL();                                                              \
-            LZ_TREE(lp_ + LEN_LOW + ((POS_STATE) << 3), 3, lv_, 7);                 \
+            LZ_TREE(lp_ + LEN_LOW + ((POS_STATE) << 3), 3, lv_, 0);                 \
             (LEN) = lv_; (WHICH) = 0;                                               \
         } else {                                                                    \
             LZ_BIT(lp_ + LEN_CHOICE2, lb_);                                         \
-            LZ_FILL();                                                              \
             if (LZ_LIKELY(lb_ == 0)) {                                              \
-                LZ_TREE(lp_ + LEN_MID + ((POS_STATE) << 3), 3, lv_, 7);             \
+                LZ_TREE(lp_ + LEN_MID + ((POS_STATE) << 3), 3, lv_, 0);             \
                 (LEN) = 8 + lv_; (WHICH) = 1;                                       \
             } else {                                                                \
-                LZ_TREE(lp_ + LEN_HIGH, 8, lv_, 0);                                 \
+                LZ_TREE(lp_ + LEN_HIGH, 8, lv_, 0x88);                              \
                 (LEN) = 16 + lv_; (WHICH) = 2;                                      \
             }                                                                       \
         }                                                                           \
@@ -371,7 +387,7 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
             uint32_t mb = matchb;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                if ((i & 3) == 3) LZ_FILL();
+                if (i == 4) LZ_FILL();
                 mb += mb;
                 const uint32_t old = offs;
                 offs &= mb;                                      // match bit, if still in matched mode
@@ -394,17 +410,17 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
         LZ_BIT(rep4 + 0, bit);                                    // isRep, :195-213
         if (bit == 0) {  // simple match, :215-668
             d.rep3 = d.rep2; d.rep2 = d.rep1; d.rep1 = d.rep0;    // :216
+            LZ_FILL();
             LZ_LEN(P + P_LEN0, pos_state, len, which);            // :218-429
             d.state = d.state < 7 ? 7 : 10;                       // stateUpdateMatch, :431
             const uint32_t len_state = len > 3 ? 3 : len;         // :434-437
             uint32_t slot;
-            LZ_TREE(P + P_POS_SLOT + (len_state << 6), 6, slot, 0);  // :441-486
+            LZ_TREE(P + P_POS_SLOT + (len_state << 6), 6, slot, 0x21);  // :441-486, fills before bits 0, 5
             if (LZ_UNLIKELY(slot < 4)) {
                 d.rep0 = slot;                                    // :488-489
             } else {
                 const uint32_t nd = (slot >> 1) - 1;
                 uint32_t dist = (2 | (slot & 1)) << nd, v;
-                LZ_FILL();
                 if (LZ_UNLIKELY(slot < 14)) {                     // :494-546
                     // own sub-table layout: slot s starts at dist - 4; the reference's is dist - slot (:496)
                     LZ_TREE_REV(P + P_POS_DEC + dist - 4, nd, v, 5);
@@ -415,7 +431,7 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
                         // DecodeDirectBits (:549-576) normalises when the halved range drops below
                         // 2^24: first after g = 8 - clz(range) halvings, then after every 8th.
                         // At most 4 normalisations for 26 bits: one top-up covers them.
-                        if (kFast) LZ_FILL(); else LZ_FILL32();
+                        LZ_FILL();
                         uint32_t n = nd - 4;                       // 1..26
                         uint32_t g = 8 - LZ_CLZ(d.range);          // 1..8 halvings to the next normalisation
 #pragma unroll 1
@@ -485,8 +501,7 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
                 if (bit == 0) {
                     dist = d.rep1; d.rep1 = d.rep0; d.rep0 = dist;
                 } else {
-                    LZ_FILL();
-                    LZ_BIT(rep4 + 3, bit);                        // isRepG2, :816-861
+                    LZ_BIT(rep4 + 3, bit);                        // isRepG2, :816-861 (5th step since the fill)
                     if (bit == 0) { dist = d.rep2; d.rep2 = d.rep1; d.rep1 = d.rep0; d.rep0 = dist; }
                     else { dist = d.rep3; d.rep3 = d.rep2; d.rep2 = d.rep1; d.rep1 = d.rep0; d.rep0 = dist; }
                 }
