@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Device-timed throughput of the decode kernel on other shapes than bench.py's headline workload:
+batch size (units per GPU), unit size, and data kind.  Inputs resident in HBM, CUDA events around
+the launches, every unit's CRC checked.  Prints one JSON line per shape."""
+import json
+import os
+import sys
+import zlib
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lzma_b200 import _lib as L  # noqa: E402
+from lzma_b200 import batch as B  # noqa: E402
+from lzma_b200 import corpus as K  # noqa: E402
+
+KINDS = {"text": K.text_block, "random": K.random_block, "mixed": K.mixed_block}
+
+
+def run(ctx, kind, n_units, size, distinct=32, steps=3):
+    plains = [KINDS[kind](1000 + i, size) for i in range(distinct)]
+    streams = [K.compress_alone(p) for p in plains]
+    pick = [i % distinct for i in range(n_units)]
+    units, in_buf, out_size, _ = B.build_alone_batch([streams[i] for i in pick], [size] * n_units)
+    d_in = torch.from_numpy(in_buf).cuda()
+    d_out = torch.empty(out_size, dtype=torch.uint8, device="cuda")
+    plan = ctx.plan(units, in_buf.nbytes, out_size)
+    st = torch.cuda.current_stream().cuda_stream or 1
+    for _ in range(2):
+        plan.launch(d_in.data_ptr(), d_out.data_ptr(), st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        plan.launch(d_in.data_ptr(), d_out.data_ptr(), st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    res, _ = plan.results()
+    out = d_out.cpu().numpy()
+    crcs = [zlib.crc32(p) for p in plains]
+    for k in range(0, n_units, max(1, n_units // 64)):
+        u = units[k]
+        assert res[k].status == L.OK and zlib.crc32(out[u.out_off:u.out_off + size]) == crcs[pick[k]]
+    comp = sum(len(streams[i]) for i in pick)
+    plan.close()
+    del d_in, d_out
+    print(json.dumps({"kind": kind, "units": n_units, "unit_bytes": size, "ratio": round(n_units * size / comp, 2),
+                      "ms": round(ms, 2), "GBps": round(n_units * size / ms / 1e6, 3)}), flush=True)
+
+
+if __name__ == "__main__":
+    with B.Context([0]) as ctx:
+        for n in (148, 592, 1024, 1924, 2048, 4096, 8192):
+            run(ctx, "text", n, 1 << 20)
+        run(ctx, "text", 2048, 4 << 20, distinct=16)      # BASELINE config 5's per-GPU shape at 8 GPUs
+        run(ctx, "random", 1024, 1 << 20)
+        run(ctx, "mixed", 1024, 1 << 20)
