@@ -201,6 +201,9 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ our arm
+    if not os.path.exists(os.path.join(ROOT, "lzma_b200", "liblzgpu.so")):
+        import __graft_entry__
+        __graft_entry__.build()      # compile the CUDA extension in-tree (nvcc cross-compiles anywhere)
     import torch
     import torch.distributed as dist
     from lzma_b200 import _lib as L
