@@ -255,9 +255,42 @@ LZ_HD int rc_init(Dec &d) {
         d.inbits -= sh_;                                                            \
     } while (0)
 
-// One adaptive bit (DecodeBit, range_decoder.go:57-98), select form.
+// One adaptive bit (DecodeBit, range_decoder.go:57-98) followed by the normalisation, select form.
 // Probability update: p + ((2048 - p) >> 5) for a 0, p - (p >> 5) for a 1; the latter equals
 // p + ((31 - p) >> 5) with an arithmetic shift, so both are p + ((k - p) >> 5).
+#if defined(__CUDA_ARCH__) && !defined(LZ_NO_PTX_BIT)
+// Device: the step spelled out in PTX so that the conditional updates are single predicated
+// instructions (the C form below compiles to select + operate pairs: ~3 more per bit).
+#define LZ_BIT(PP, BIT)                                                             \
+    do {                                                                            \
+        uint16_t *pp_ = (PP);                                                       \
+        const uint32_t p_ = *pp_;                                                   \
+        uint32_t pn_, b01_;                                                         \
+        asm("{\n\t.reg .pred one, nz;\n\t.reg .b32 bd, t, k;\n\t"                   \
+            "shr.u32 t, %0, 11;\n\t"                                                \
+            "mul.lo.u32 bd, t, %7;\n\t"                                             \
+            "setp.ge.u32 one, %1, bd;\n\t"                                          \
+            "sub.u32 t, %0, bd;\n\t"                                                \
+            "selp.b32 %0, t, bd, one;\n\t"                                          \
+            "@one sub.u32 %1, %1, bd;\n\t"                                          \
+            "selp.b32 k, 31, 2048, one;\n\t"                                        \
+            "sub.s32 k, k, %7;\n\t"                                                 \
+            "shr.s32 k, k, 5;\n\t"                                                  \
+            "add.s32 %6, %7, k;\n\t"                                                \
+            "selp.u32 %5, 1, 0, one;\n\t"                                           \
+            "setp.lt.u32 nz, %0, 0x1000000;\n\t"                                    \
+            "@nz shl.b32 %0, %0, 8;\n\t"                                            \
+            "@nz shf.l.wrap.b32 %1, %2, %1, 8;\n\t"                                 \
+            "@nz shf.l.wrap.b32 %2, %3, %2, 8;\n\t"                                 \
+            "@nz shl.b32 %3, %3, 8;\n\t"                                            \
+            "@nz add.u32 %4, %4, -8;\n\t}"                                          \
+            : "+r"(d.range), "+r"(d.code), "+r"(d.inb_hi), "+r"(d.inb_lo), "+r"(d.inbits), \
+              "=r"(b01_), "=r"(pn_)                                                 \
+            : "r"(p_));                                                             \
+        *pp_ = (uint16_t)pn_;                                                       \
+        (BIT) = b01_;                                                               \
+    } while (0)
+#else
 #define LZ_BIT(PP, BIT)                                                             \
     do {                                                                            \
         uint16_t *pp_ = (PP);                                                       \
@@ -270,6 +303,7 @@ LZ_HD int rc_init(Dec &d) {
         (BIT) = one_ ? 1u : 0u;                                                     \
         LZ_NORM();                                                                  \
     } while (0)
+#endif
 
 // One equiprobable bit (DecodeDirectBits, range_decoder.go:100-134 / decompress.go:549-576)
 #define LZ_DIRECT(RES)                                                              \
