@@ -477,10 +477,22 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
                             uint32_t acc = 0;
 #pragma unroll
                             for (uint32_t j = 1; j <= 8; j++) {
+#if defined(__CUDA_ARCH__) && !defined(LZ_NO_PTX_BIT)
+                                // 5 instructions per step: the compare carries the "step is live" test
+                                asm("{\n\t.reg .pred live, one;\n\t.reg .b32 rj;\n\t"
+                                    "setp.le.u32 live, %3, %4;\n\t"
+                                    "shr.u32 rj, %2, %3;\n\t"
+                                    "setp.ge.and.u32 one, %0, rj, live;\n\t"
+                                    "@one sub.u32 %0, %0, rj;\n\t"
+                                    "@one or.b32 %1, %1, %5;\n\t}"
+                                    : "+r"(d.code), "+r"(acc)
+                                    : "r"(r0), "r"(j), "r"(k), "r"(1u << (8 - j)));
+#else
                                 const uint32_t rj = r0 >> j;
                                 const bool one = (j <= k) && d.code >= rj;
                                 d.code -= one ? rj : 0u;
                                 acc |= one ? (1u << (8 - j)) : 0u;
+#endif
                             }
                             d.range = r0 >> k;
                             res = (res << k) | (acc >> (8 - k));
