@@ -290,6 +290,37 @@ LZ_HD int rc_init(Dec &d) {
         *pp_ = (uint16_t)pn_;                                                       \
         (BIT) = b01_;                                                               \
     } while (0)
+// matched-literal flavour: additionally OFFS ^= (bit ? 0 : OLD) as one predicated xor
+#define LZ_BIT_MLIT(PP, BIT, OFFS, OLD)                                             \
+    do {                                                                            \
+        uint16_t *pp_ = (PP);                                                       \
+        const uint32_t p_ = *pp_;                                                   \
+        uint32_t pn_, b01_;                                                         \
+        asm("{\n\t.reg .pred one, nz;\n\t.reg .b32 bd, t, k;\n\t"                   \
+            "shr.u32 t, %0, 11;\n\t"                                                \
+            "mul.lo.u32 bd, t, %8;\n\t"                                             \
+            "setp.ge.u32 one, %1, bd;\n\t"                                          \
+            "sub.u32 t, %0, bd;\n\t"                                                \
+            "selp.b32 %0, t, bd, one;\n\t"                                          \
+            "@one sub.u32 %1, %1, bd;\n\t"                                          \
+            "@!one xor.b32 %7, %7, %9;\n\t"                                         \
+            "selp.b32 k, 31, 2048, one;\n\t"                                        \
+            "sub.s32 k, k, %8;\n\t"                                                 \
+            "shr.s32 k, k, 5;\n\t"                                                  \
+            "add.s32 %6, %8, k;\n\t"                                                \
+            "selp.u32 %5, 1, 0, one;\n\t"                                           \
+            "setp.lt.u32 nz, %0, 0x1000000;\n\t"                                    \
+            "@nz shl.b32 %0, %0, 8;\n\t"                                            \
+            "@nz shf.l.wrap.b32 %1, %2, %1, 8;\n\t"                                 \
+            "@nz shf.l.wrap.b32 %2, %3, %2, 8;\n\t"                                 \
+            "@nz shl.b32 %3, %3, 8;\n\t"                                            \
+            "@nz add.u32 %4, %4, -8;\n\t}"                                          \
+            : "+r"(d.range), "+r"(d.code), "+r"(d.inb_hi), "+r"(d.inb_lo), "+r"(d.inbits), \
+              "=r"(b01_), "=r"(pn_), "+r"(OFFS)                                     \
+            : "r"(p_), "r"(OLD));                                                   \
+        *pp_ = (uint16_t)pn_;                                                       \
+        (BIT) = b01_;                                                               \
+    } while (0)
 #else
 #define LZ_BIT(PP, BIT)                                                             \
     do {                                                                            \
@@ -302,6 +333,11 @@ LZ_HD int rc_init(Dec &d) {
         *pp_ = (uint16_t)(p_ + (uint32_t)((int32_t)((one_ ? 31u : 2048u) - p_) >> 5)); \
         (BIT) = one_ ? 1u : 0u;                                                     \
         LZ_NORM();                                                                  \
+    } while (0)
+#define LZ_BIT_MLIT(PP, BIT, OFFS, OLD)                                             \
+    do {                                                                            \
+        LZ_BIT(PP, BIT);                                                            \
+        (OFFS) ^= (BIT) ? 0u : (OLD);                                               \
     } while (0)
 #endif
 
@@ -425,9 +461,8 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
                 mb += mb;
                 const uint32_t old = offs;
                 offs &= mb;                                      // match bit, if still in matched mode
-                LZ_BIT(pr + offs + old + sym, bit);
+                LZ_BIT_MLIT(pr + offs + old + sym, bit, offs, old);   // offs stays set only while bit == match bit
                 sym = (sym << 1) | bit;
-                offs ^= bit ? 0u : old;                          // stays set only while bit == match bit
             }
             if (LZ_UNLIKELY(LZ_EXHAUSTED())) goto input_eof;
             sym &= 0xFF;
