@@ -135,8 +135,10 @@ def cpu_pass(blob, offs, lens, sample_idx, size, threads):
     return time.perf_counter() - t0, bad
 
 
-def cpu_sample(distinct: int, cores: int):
-    n = max(32, min(distinct, cores * 4))
+def cpu_sample(distinct: int, cores: int, streams: int = 1024):
+    """Bounded sample of the workload for the CPU legs: ~1 s of wall time on all cores
+    (about 35 ms of one core per 1 MiB stream -> 10-30 core-seconds)."""
+    n = max(32, min(streams, cores * 32))
     return np.arange(n) % distinct
 
 
@@ -178,7 +180,7 @@ def main():
         if rank != 0:
             return 0
         blob, offs, lens, _ = build_corpus(distinct, args.size)
-        idx = cpu_sample(distinct, cores)
+        idx = cpu_sample(distinct, cores, args.streams)
         for _ in range(args.warmup):
             cpu_pass(blob, offs, lens, idx, args.size, cores)
         t = 0.0
@@ -374,7 +376,7 @@ def main():
                            "rank0_breakdown_ms": {"h2d": e2e["h2d_ms"], "kernel": e2e["kernel_ms"], "d2h": e2e["d2h_ms"]},
                            "api": "lzgpu_decode_batch (pinned host buffers)"}
         if world == 1 and not args.no_cpu_baseline:
-            idx = cpu_sample(distinct, cores)
+            idx = cpu_sample(distinct, cores, args.streams)
             cpu_pass(blob, offs, lens, idx[:max(1, len(idx) // 4)], args.size, cores)  # warm
             dt, nbad = cpu_pass(blob, offs, lens, idx, args.size, cores)
             assert nbad == 0
