@@ -73,6 +73,7 @@ static void launch_decode(int variant, unsigned grid, size_t smem, cudaStream_t 
     switch (variant) {
         case 3: lzgpu_decode_kernel<kLitGlobal, 3><<<grid, 32, smem, st>>>(a); break;
         case 11: lzgpu_decode_kernel<kLitGlobal, 11><<<grid, 32, smem, st>>>(a); break;
+        case 15: lzgpu_decode_kernel<kLitGlobal, 15><<<grid, 32, smem, st>>>(a); break;
         default: lzgpu_decode_kernel<kLitGlobal, 0><<<grid, 32, smem, st>>>(a); break;
     }
 }

@@ -165,7 +165,10 @@ LZ_HD void rc_fill(Dec &d) {
 //   V_UNIFORM      all 32 lanes run the serial decoder redundantly on identical data instead of
 //                  lane 0 alone: same issue cost (SIMT), but no divergence entry/exit and no
 //                  shuffles per match; same-address shared/global accesses are broadcasts
-enum : int { V_FAST = 1, V_DIRECT_GROUP = 2, V_UNIFORM = 8 };
+//   V_PREFETCH     bit trees fetch BOTH children of the current node (one aligned 32-bit LDS)
+//                  before the bit is known: shared-memory latency leaves the serial chain, at
+//                  two more instructions per bit (helps a lone warp, not a contended one)
+enum : int { V_FAST = 1, V_DIRECT_GROUP = 2, V_PREFETCH = 4, V_UNIFORM = 8 };
 constexpr uint32_t kFastInMargin = 64;    // >= 48 bit steps of one symbol + one word loaded ahead + slack
 constexpr uint32_t kFastOutMargin = 274;  // longest match is 273
 
@@ -261,10 +264,11 @@ LZ_HD int rc_init(Dec &d) {
 #if defined(__CUDA_ARCH__) && !defined(LZ_NO_PTX_BIT)
 // Device: the step spelled out in PTX so that the conditional updates are single predicated
 // instructions (the C form below compiles to select + operate pairs: ~3 more per bit).
-#define LZ_BIT(PP, BIT)                                                             \
+#define LZ_BIT(PP, BIT) LZ_BIT_V(PP, *(PP), BIT)
+#define LZ_BIT_V(PP, PVAL, BIT)                                                     \
     do {                                                                            \
         uint16_t *pp_ = (PP);                                                       \
-        const uint32_t p_ = *pp_;                                                   \
+        const uint32_t p_ = (PVAL);                                                 \
         uint32_t pn_, b01_;                                                         \
         asm("{\n\t.reg .pred one, nz;\n\t.reg .b32 bd, t, k;\n\t"                   \
             "shr.u32 t, %0, 11;\n\t"                                                \
@@ -322,10 +326,11 @@ LZ_HD int rc_init(Dec &d) {
         (BIT) = b01_;                                                               \
     } while (0)
 #else
-#define LZ_BIT(PP, BIT)                                                             \
+#define LZ_BIT(PP, BIT) LZ_BIT_V(PP, *(PP), BIT)
+#define LZ_BIT_V(PP, PVAL, BIT)                                                     \
     do {                                                                            \
         uint16_t *pp_ = (PP);                                                       \
-        const uint32_t p_ = *pp_;                                                   \
+        const uint32_t p_ = (PVAL);                                                 \
         const uint32_t bound_ = (d.range >> 11) * p_;                               \
         const bool one_ = d.code >= bound_;                                         \
         d.range = one_ ? d.range - bound_ : bound_;                                 \
@@ -351,16 +356,33 @@ LZ_HD int rc_init(Dec &d) {
         LZ_NORM();                                                                  \
     } while (0)
 
+// Children of node m are entries 2m and 2m+1: one aligned 32-bit load (all P_* bases and
+// sub-table strides are even, the shared array is 16-byte aligned).
+#define LZ_PAIR(TP, M) (*reinterpret_cast<const uint32_t *>((TP) + 2u * (M)))
+#define LZ_PICK(PAIR, BIT) (((PAIR) >> ((BIT) << 4)) & 0xFFFFu)
+
 // MSB-first bit tree (BitTreeDecode, bit_tree_decoder.go:26-76), NBITS constant, unrolled.
 // FILL_MASK: bit i set = top the lookahead up before tree bit i.
-#define LZ_TREE(PROBS, NBITS, OUT, FILL_MASK)                                         \
+#define LZ_TREE(PROBS, NBITS, OUT, FILL_MASK)                                       \
     do {                                                                            \
         uint16_t *tp_ = (PROBS);                                                    \
         uint32_t m_ = 1, b_;                                                        \
-        _Pragma("unroll") for (int i_ = 0; i_ < (NBITS); i_++) {                    \
-            if (((FILL_MASK) >> i_) & 1) LZ_FILL();                                 \
-            LZ_BIT(tp_ + m_, b_);                                                   \
-            m_ = (m_ << 1) | b_;                                                    \
+        if (kV & V_PREFETCH) {                                                      \
+            uint32_t pv_ = tp_[1];                                                  \
+            _Pragma("unroll") for (int i_ = 0; i_ < (NBITS); i_++) {                \
+                if (((FILL_MASK) >> i_) & 1) LZ_FILL();                             \
+                uint32_t pair_ = 0;                                                 \
+                if (i_ + 1 < (NBITS)) pair_ = LZ_PAIR(tp_, m_);                     \
+                LZ_BIT_V(tp_ + m_, pv_, b_);                                        \
+                m_ = (m_ << 1) | b_;                                                \
+                pv_ = LZ_PICK(pair_, b_);                                           \
+            }                                                                       \
+        } else {                                                                    \
+            _Pragma("unroll") for (int i_ = 0; i_ < (NBITS); i_++) {                \
+                if (((FILL_MASK) >> i_) & 1) LZ_FILL();                             \
+                LZ_BIT(tp_ + m_, b_);                                               \
+                m_ = (m_ << 1) | b_;                                                \
+            }                                                                       \
         }                                                                           \
         (OUT) = m_ - (1u << (NBITS));                                               \
     } while (0)
@@ -371,12 +393,27 @@ LZ_HD int rc_init(Dec &d) {
         uint16_t *tp_ = (PROBS);                                                    \
         uint32_t m_ = 1, b_, s_ = 0;                                                \
         const uint32_t nb_ = (NBITS);                                               \
-        _Pragma("unroll") for (uint32_t i_ = 0; i_ < (MAXBITS); i_++) {             \
-            if (i_ < nb_) {                                                         \
-                if (i_ == 4) LZ_FILL();                                             \
-                LZ_BIT(tp_ + m_, b_);                                               \
-                m_ = (m_ << 1) | b_;                                                \
-                s_ |= b_ << i_;                                                     \
+        if (kV & V_PREFETCH) {                                                      \
+            uint32_t pv_ = tp_[1];                                                  \
+            _Pragma("unroll") for (uint32_t i_ = 0; i_ < (MAXBITS); i_++) {         \
+                if (i_ < nb_) {                                                     \
+                    if (i_ == 4) LZ_FILL();                                         \
+                    uint32_t pair_ = 0;                                             \
+                    if (i_ + 1 < nb_) pair_ = LZ_PAIR(tp_, m_);                     \
+                    LZ_BIT_V(tp_ + m_, pv_, b_);                                    \
+                    m_ = (m_ << 1) | b_;                                            \
+                    s_ |= b_ << i_;                                                 \
+                    pv_ = LZ_PICK(pair_, b_);                                       \
+                }                                                                   \
+            }                                                                       \
+        } else {                                                                    \
+            _Pragma("unroll") for (uint32_t i_ = 0; i_ < (MAXBITS); i_++) {         \
+                if (i_ < nb_) {                                                     \
+                    if (i_ == 4) LZ_FILL();                                         \
+                    LZ_BIT(tp_ + m_, b_);                                           \
+                    m_ = (m_ << 1) | b_;                                            \
+                    s_ |= b_ << i_;                                                 \
+                }                                                                   \
             }                                                                       \
         }                                                                           \
         (OUT) = s_;                                                                 \

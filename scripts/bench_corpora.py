@@ -53,6 +53,10 @@ def run(ctx, kind, n_units, size, distinct=32, steps=3):
 
 if __name__ == "__main__":
     with B.Context([0]) as ctx:
+        if "--quick" in sys.argv:          # A/B of tuning variants: lone-warp latency and the bench shape
+            for n in (148, 1024):
+                run(ctx, "text", n, 1 << 20)
+            sys.exit(0)
         for n in (148, 592, 1024, 1924, 2048, 4096, 8192):
             run(ctx, "text", n, 1 << 20)
         run(ctx, "text", 2048, 4 << 20, distinct=16)      # BASELINE config 5's per-GPU shape at 8 GPUs

@@ -46,6 +46,7 @@ extern "C" int emu_decode_batch(const lzgpu_unit *units, int64_t n, const uint8_
         switch (variant) {
             case 3: run_one<3>(u, io, P, L, bits, r); break;
             case 11: run_one<11>(u, io, P, L, bits, r); break;
+            case 15: run_one<15>(u, io, P, L, bits, r); break;
             default: run_one<0>(u, io, P, L, bits, r); break;
         }
         if (alone) r.bytes_in += 13;
