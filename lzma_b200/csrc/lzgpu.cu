@@ -24,7 +24,7 @@
 using namespace lzgpu;
 
 #ifndef LZGPU_DEFAULT_VARIANT
-#define LZGPU_DEFAULT_VARIANT 11
+#define LZGPU_DEFAULT_VARIANT 1
 #endif
 
 // ------------------------------------------------------------------ kernel
@@ -38,6 +38,7 @@ struct KArgs {
     uint64_t lit_ws_stride;      // uint16 elements per slot
     uint32_t lit_bits_cap;       // literal-table capacity of this launch, as lc+lp
     uint32_t slot0;              // first slot of this launch in `order`
+    uint32_t stage_off;          // uint16 index of the 64-byte staging buffer inside the shared array
 };
 
 // One warp per CTA, one unit per warp.  Fixed tables (3.7 KB) always in shared
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(32) lzgpu_decode_kernel(const KArgs a) {
     io.in_len = u.in_len;
     io.out = a.out_base + u.out_off;
     io.out_cap = u.out_cap;
+    io.stage = reinterpret_cast<uint8_t *>(smem_probs + a.stage_off);
     lzgpu_result &res = a.results[ui];
     if (u.kind == LZGPU_KIND_LZMA2_GROUP) run_unit_lzma2<kV>(u, io, P, L, a.lit_bits_cap, res);
     else run_unit_lzma1<kV>(u, io, P, L, res);
@@ -71,10 +73,11 @@ static int decoder_variant() {
 template <bool kLitGlobal>
 static void launch_decode(int variant, unsigned grid, size_t smem, cudaStream_t st, const KArgs &a) {
     switch (variant) {
-        case 3: lzgpu_decode_kernel<kLitGlobal, 3><<<grid, 32, smem, st>>>(a); break;
-        case 11: lzgpu_decode_kernel<kLitGlobal, 11><<<grid, 32, smem, st>>>(a); break;
-        case 15: lzgpu_decode_kernel<kLitGlobal, 15><<<grid, 32, smem, st>>>(a); break;
-        default: lzgpu_decode_kernel<kLitGlobal, 0><<<grid, 32, smem, st>>>(a); break;
+        case 0: lzgpu_decode_kernel<kLitGlobal, 0><<<grid, 32, smem, st>>>(a); break;
+        case 5: lzgpu_decode_kernel<kLitGlobal, 5><<<grid, 32, smem, st>>>(a); break;
+        case 17: lzgpu_decode_kernel<kLitGlobal, 17><<<grid, 32, smem, st>>>(a); break;
+        case 21: lzgpu_decode_kernel<kLitGlobal, 21><<<grid, 32, smem, st>>>(a); break;
+        default: lzgpu_decode_kernel<kLitGlobal, 1><<<grid, 32, smem, st>>>(a); break;
     }
 }
 
@@ -350,8 +353,12 @@ extern "C" void lzgpu_plan_destroy(lzgpu_plan *p) {
     delete p;
 }
 
+// shared memory of one unit: probability tables, then 64 bytes of window-copy staging
+static size_t probs_elems(uint32_t lit_bits, bool lit_global) {
+    return (size_t)P_FIXED + (lit_global ? 0 : ((size_t)0x300 << lit_bits));
+}
 static size_t smem_bytes(uint32_t lit_bits, bool lit_global) {
-    return sizeof(uint16_t) * ((size_t)P_FIXED + (lit_global ? 0 : ((size_t)0x300 << lit_bits)));
+    return sizeof(uint16_t) * probs_elems(lit_bits, lit_global) + 64;
 }
 
 extern "C" int lzgpu_plan_create(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *units, int64_t n,
@@ -469,6 +476,7 @@ extern "C" int lzgpu_plan_launch(lzgpu_plan *p, const uint8_t *d_in, uint8_t *d_
         a.lit_ws_stride = p->lit_ws_stride;
         a.lit_bits_cap = L.lit_bits;
         a.slot0 = L.slot0;
+        a.stage_off = (uint32_t)probs_elems(L.lit_bits, L.lit_global);
         if (L.lit_global) launch_decode<true>(p->variant, L.count, L.smem, st, a);
         else launch_decode<false>(p->variant, L.count, L.smem, st, a);
         CUDA_TRY(cudaGetLastError());

@@ -21,6 +21,7 @@
 // (test infrastructure; never linked into liblzgpu.so).
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/lzgpu.h"
 
@@ -31,6 +32,7 @@
 #endif
 
 #if defined(__CUDA_ARCH__)
+#define LZ_WARP_SYNC() __syncwarp()
 #define LZ_LD_IN8(p) __ldg(reinterpret_cast<const unsigned char *>(p))
 #define LZ_LD_IN32(p) __ldg(reinterpret_cast<const unsigned int *>(p))
 #define LZ_BSWAP32(x) __byte_perm((x), 0u, 0x0123u)
@@ -40,6 +42,12 @@
 #define LZ_FUNNEL_R(lo, hi, sh) __funnelshift_r((lo), (hi), (sh))   /* ((hi:lo) >> (sh & 31)) low word */
 #define LZ_SHR_CLAMP(x, sh) __funnelshift_rc((x), 0u, (sh))          /* x >> min(sh, 32) */
 // predicated global load: no branch, so lane 0's instruction stream stays straight-line
+// cp.async (LDGSTS): 4 aligned bytes global -> shared with no register and no scoreboard involved;
+// completion is awaited explicitly (wait_group) where the bytes are needed
+#define LZ_CP_ASYNC4(sdst, gsrc)                                                        \
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory")
+#define LZ_CP_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
+#define LZ_CP_WAIT() asm volatile("cp.async.wait_group 0;" ::: "memory")
 // window byte -> 32-bit register, issued now, first touched when a literal needs it (anything
 // the compiler inserts in between -- a mask, a move -- would stall on the load right here)
 #define LZ_LD_WIN8(dst, p) asm volatile("ld.global.u8 %0, [%1];" : "=r"(dst) : "l"(p) : "memory")
@@ -49,6 +57,7 @@
 #define LZ_LIKELY(x) __builtin_expect(!!(x), 1)
 #define LZ_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #else
+#define LZ_WARP_SYNC() ((void)0)
 #define LZ_LD_IN8(p) (*(const uint8_t *)(p))
 #define LZ_LD_IN32(p) (*(const uint32_t *)(p))
 #define LZ_BSWAP32(x) __builtin_bswap32(x)
@@ -59,6 +68,9 @@
 #define LZ_SHR_CLAMP(x, sh) ((sh) >= 32 ? 0u : ((uint32_t)(x) >> (sh)))
 #define LZ_LD_IN32_IF(dst, p, cond) do { if (cond) (dst) = *(const uint32_t *)(p); } while (0)
 #define LZ_LD_WIN8(dst, p) ((dst) = *(const uint8_t *)(p))
+#define LZ_CP_ASYNC4(sdst, gsrc) memcpy((sdst), (gsrc), 4)   /* value captured at issue, like the copy */
+#define LZ_CP_COMMIT() ((void)0)
+#define LZ_CP_WAIT() ((void)0)
 #define LZ_LIKELY(x) __builtin_expect(!!(x), 1)
 #define LZ_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #endif
@@ -105,8 +117,9 @@ struct Dec {
     uint32_t size_defined;          // state.unpackSizeDefined
     uint32_t lc, lp_mask, pos_mask;
     uint32_t prev_byte, mbyte;      // literal context: byte at -1 and at -(rep0+1)
-    uint32_t ctx_a, ctx_b;          // the same two bytes when a window copy has just loaded them ...
-    uint32_t ctx_pending;           // ... (then they supersede prev_byte / mbyte at the next literal)
+    uint32_t ctx_a, ctx_b;          // the same two bytes when a window copy has just fetched them:
+    uint32_t ctx_pending;           // 1 = values loaded into ctx_a/b, 2 = offsets into `stage` (cp.async)
+    const uint8_t *stage;           // V_STAGE: the warp's shared staging buffer for window-copy sources
     int32_t status, site;
 };
 
@@ -158,17 +171,16 @@ LZ_HD void rc_fill(Dec &d) {
 //         word that was loaded one top-up earlier.  Taken branches cost a lone warp an
 //         instruction-fetch bubble each (ncu: stall_no_instructions), hence the effort.
 //         The careful decoder (kFast = false) handles the head and tail of a unit.
-//  kV tuning variants, chosen per launch:
-//   V_FAST         allow the fast decoder at all
-//   V_DIRECT_GROUP equiprobable bits in runs between two normalisations (their position is
-//                  known from the range's leading zeros) instead of a full step per bit
-//   V_UNIFORM      all 32 lanes run the serial decoder redundantly on identical data instead of
-//                  lane 0 alone: same issue cost (SIMT), but no divergence entry/exit and no
-//                  shuffles per match; same-address shared/global accesses are broadcasts
-//   V_PREFETCH     bit trees fetch BOTH children of the current node (one aligned 32-bit LDS)
-//                  before the bit is known: shared-memory latency leaves the serial chain, at
-//                  two more instructions per bit (helps a lone warp, not a contended one)
-enum : int { V_FAST = 1, V_DIRECT_GROUP = 2, V_PREFETCH = 4, V_UNIFORM = 8 };
+//  kV tuning variants, chosen per launch (LZGPU_VARIANT):
+//   V_FAST      allow the fast decoder at all (off: the careful decoder runs everywhere -- a test
+//               mode that drives every stream through the tail/error-checking code)
+//   V_PREFETCH  bit trees fetch BOTH children of the current node (one aligned 32-bit LDS) before
+//               the bit is known: shared-memory latency leaves the serial chain at two more
+//               instructions per bit (helps a lone warp, not a contended one)
+//   V_STAGE     window-copy sources are staged in shared memory by cp.async instead of being held
+//               in registers until the deferred store: no load result is outstanding when the
+//               decoder resumes, so nothing in it can be made to wait on the window
+enum : int { V_FAST = 1, V_PREFETCH = 4, V_STAGE = 16 };
 constexpr uint32_t kFastInMargin = 64;    // >= 48 bit steps of one symbol + one word loaded ahead + slack
 constexpr uint32_t kFastOutMargin = 274;  // longest match is 273
 
@@ -346,16 +358,6 @@ LZ_HD int rc_init(Dec &d) {
     } while (0)
 #endif
 
-// One equiprobable bit (DecodeDirectBits, range_decoder.go:100-134 / decompress.go:549-576)
-#define LZ_DIRECT(RES)                                                              \
-    do {                                                                            \
-        d.range >>= 1;                                                              \
-        const bool one_ = d.code >= d.range;                                        \
-        d.code = one_ ? d.code - d.range : d.code;                                  \
-        (RES) = ((RES) << 1) | (one_ ? 1u : 0u);                                    \
-        LZ_NORM();                                                                  \
-    } while (0)
-
 // Children of node m are entries 2m and 2m+1: one aligned 32-bit load (all P_* bases and
 // sub-table strides are even, the shared array is 16-byte aligned).
 #define LZ_PAIR(TP, M) (*reinterpret_cast<const uint32_t *>((TP) + 2u * (M)))
@@ -481,8 +483,18 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
             }
             // context bytes: straight from the last window copy's loads if there was one (first use
             // of those registers, so this is where a literal-after-match waits for the window)
-            const uint32_t prevb = d.ctx_pending ? d.ctx_a : d.prev_byte;
-            const uint32_t matchb = d.ctx_pending ? d.ctx_b : d.mbyte;
+            uint32_t prevb = d.prev_byte, matchb = d.mbyte;
+            if ((kV & V_STAGE) && d.ctx_pending == 2) {
+                // staged by cp.async: every lane waits for its own chunks, then the warp syncs so
+                // that each lane may read what the others fetched (all lanes are here together)
+                LZ_CP_WAIT();
+                LZ_WARP_SYNC();
+                prevb = d.stage[d.ctx_a];
+                matchb = d.stage[d.ctx_b];
+            } else if (d.ctx_pending) {
+                prevb = d.ctx_a;
+                matchb = d.ctx_b;
+            }
             d.ctx_pending = 0;
             uint16_t *pr = L + 0x300u * (((d.wpos & d.lp_mask) << d.lc) + (prevb >> (8 - d.lc)));  // :56-57
             // Plain and matched literals in one straight-line tree walk: `offs` is 0x100 while
@@ -533,7 +545,7 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
                     dist += v;
                 } else {                                          // :548-628
                     uint32_t res = 0;
-                    if (kV & V_DIRECT_GROUP) {
+                    {
                         // DecodeDirectBits (:549-576) normalises when the halved range drops below
                         // 2^24: first after g = 8 - clz(range) halvings, then after every 8th.
                         // At most 4 normalisations for 26 bits: one top-up covers them.
@@ -572,11 +584,6 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
                             if (k == g) LZ_SHIFT8();
                             g = 8;
                             if (n == 0) break;
-                        }
-                    } else {
-                        for (uint32_t n = nd - 4; n > 0; n--) {   // DecodeDirectBits, :549-576
-                            if ((n & 3) == 0) LZ_FILL();
-                            LZ_DIRECT(res);
                         }
                     }
                     dist += res << 4;

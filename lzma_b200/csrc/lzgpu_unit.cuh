@@ -1,8 +1,10 @@
 // lzgpu_unit.cuh -- one warp decodes one unit.
 //
 // Written once in "warp-uniform" style and compiled two ways:
-//   * device (nvcc): the 32 lanes of a warp execute it together; lane 0 runs the
-//     serial range decoder, all lanes copy;
+//   * device (nvcc): the 32 lanes of a warp execute it together: every lane runs the serial
+//     range decoder redundantly on identical data (same issue cost under SIMT, no divergence,
+//     nothing to broadcast; same-address shared / global accesses are broadcasts), and each lane
+//     moves its own byte of a window copy;
 //   * host lane emulation (tests/emu/, test infrastructure only): LZ_FOR_LANES
 //     loops over 32 virtual lanes and per-lane variables become arrays, so the
 //     protocol (deferred stores, what lane 0 may read when) can be checked
@@ -17,22 +19,15 @@
 #if defined(__CUDA_ARCH__)
 #define LZ_LANE() (threadIdx.x & 31u)
 #define LZ_FOR_LANES(l) for (uint32_t l = LZ_LANE(), once_ = 1; once_; once_ = 0)
-// the serial decoder runs on lane 0 only, or (V_UNIFORM) redundantly on every lane
-#define LZ_IF_LANE0 if ((kV & V_UNIFORM) || LZ_LANE() == 0)
 #define LZ_IF_LANE0_ONLY if (LZ_LANE() == 0)
 #define LZ_SYNC() __syncwarp()
-#define LZ_BCAST32(x) do { if (!(kV & V_UNIFORM)) (x) = __shfl_sync(0xffffffffu, (x), 0); } while (0)
-#define LZ_BCAST64(x) do { if (!(kV & V_UNIFORM)) (x) = __shfl_sync(0xffffffffu, (x), 0); } while (0)
 #define LZ_LANEVAR(T, name) T name
 #define LZ_LV(name, l) name
 #define LZ_DEV __device__ __forceinline__
 #else
 #define LZ_FOR_LANES(l) for (uint32_t l = 0; l < 32; l++)
-#define LZ_IF_LANE0
 #define LZ_IF_LANE0_ONLY
 #define LZ_SYNC() ((void)0)
-#define LZ_BCAST32(x) ((void)0)
-#define LZ_BCAST64(x) ((void)0)
 #define LZ_LANEVAR(T, name) T name[32]
 #define LZ_LV(name, l) name[l]
 #define LZ_DEV inline
@@ -40,18 +35,35 @@
 
 namespace lzgpu {
 
-// Uniform (same in every lane) copy bookkeeping + the per-lane deferred byte.
+// Window-copy bookkeeping (same in every lane) + the per-lane deferred byte.
 struct WarpCopy {
-    uint32_t pend_len;   // bytes loaded but not yet stored (0..32)
+    uint32_t pend_len;     // bytes fetched but not yet stored (0..32)
     uint8_t *pend_dst;
+    uint32_t pend_staged;  // the bytes wait in `stage` (cp.async) rather than in pend_val
+    uint32_t pend_off;     // staged: offset of the source's first byte in `stage`
+    uint32_t pend_dist;    // staged: match distance (period of an overlapping copy)
+    uint8_t *stage;        // 64-byte shared staging buffer of the warp (V_STAGE)
+    uint8_t *out_limit;    // end of the unit's output range (staging over-reads <= 3 bytes)
     LZ_LANEVAR(uint8_t, pend_val);
 };
 
+// Store the previous match's bytes.  They reach memory before anything can read them: this runs
+// ahead of every window fetch.
 LZ_DEV void wc_commit(WarpCopy &wc) {
-    LZ_FOR_LANES(l) {
-        if (l < wc.pend_len) wc.pend_dst[l] = LZ_LV(wc.pend_val, l);
+    if (wc.pend_len) {
+        if (wc.pend_staged) {
+            LZ_CP_WAIT();
+            LZ_SYNC();   // each lane reads bytes other lanes' cp.async fetched
+            LZ_FOR_LANES(l) {
+                if (l < wc.pend_len) wc.pend_dst[l] = wc.stage[wc.pend_off + src_index(l, wc.pend_dist)];
+            }
+        } else {
+            LZ_FOR_LANES(l) {
+                if (l < wc.pend_len) wc.pend_dst[l] = LZ_LV(wc.pend_val, l);
+            }
+        }
+        wc.pend_len = 0;
     }
-    wc.pend_len = 0;
     LZ_SYNC();
 }
 
@@ -81,114 +93,98 @@ LZ_DEV void set_props(Dec &d, uint32_t lc, uint32_t lp, uint32_t pb) {
 // store is pending.
 template <int kV>
 LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8_t *dict_base) {
-    bool fast = false;   // lane 0: which decoder runs (lzgpu_core.cuh, kFast)
+    bool fast = false;   // which decoder runs (lzgpu_core.cuh, kFast)
     set_fast_limits(d);
+    d.stage = wc.stage;
     for (;;) {
-        uint32_t op = OP_DONE, len = 0, dist = 0;
-        uint64_t dstbits = 0;
-        LZ_IF_LANE0 {
-            for (;;) {
-                if (fast) {
-                    op = decode_run<kV, true>(d, P, L, len, dist);
-                    if (op != OP_SWITCH) break;
-                    d.ip -= 4;                       // forget the word loaded ahead
-                    fast = false;
-                } else {
-                    op = decode_run<kV, false>(d, P, L, len, dist);
-                    if (op != OP_SWITCH) break;
-                    d.nextw = LZ_LD_IN32(d.ip);      // fast decoder keeps one aligned word in hand
-                    d.ip += 4;
-                    fast = true;
-                }
+        uint32_t op, len = 0, dist = 0;
+        for (;;) {
+            if (fast) {
+                op = decode_run<kV, true>(d, P, L, len, dist);
+                if (op != OP_SWITCH) break;
+                d.ip -= 4;                       // forget the word loaded ahead
+                fast = false;
+            } else {
+                op = decode_run<kV, false>(d, P, L, len, dist);
+                if (op != OP_SWITCH) break;
+                d.nextw = LZ_LD_IN32(d.ip);      // fast decoder keeps one aligned word in hand
+                d.ip += 4;
+                fast = true;
             }
-            dstbits = (uint64_t)(uintptr_t)d.outp;
         }
-        uint32_t pk = op | (len << 2);
-        LZ_BCAST32(pk);
-        op = pk & 3u;
-        len = pk >> 2;
         if (op == OP_DONE) break;
-        LZ_BCAST32(dist);
-        LZ_BCAST64(dstbits);
-        uint8_t *dst = (uint8_t *)(uintptr_t)dstbits;
+        uint8_t *dst = d.outp;
 
-        wc_commit(wc);  // the previous match's bytes reach memory before anything reads them
+        wc_commit(wc);
 
         if (op == OP_COPY) {
-            // dist > len (warp-uniform): no byte of the match depends on the match itself and
-            // byte i simply comes from dst[i - dist]; otherwise the source repeats with period dist.
+            // Byte i of the match comes from src[src_index(i)], always a byte that predates the match
+            // (period-dist replication when the match overlaps itself, window.go:73-86).
             const uint8_t *src = dst - dist;
-            const uint8_t *cprev, *cmatch;   // where the context bytes for a following literal live
-            if (LZ_LIKELY(dist > len)) {
+            const bool far = dist > len;   // the common case: src_index(i) == i
+            if ((kV & V_STAGE) && len <= 32 && dst + len + 4 <= wc.out_limit) {
+                // cp.async the 4-byte-aligned words covering src[0 .. need) into shared memory; the
+                // stores (wc_commit) and a following literal's context bytes read them from there.
+                const uint32_t need = far ? len + 1 : dist;      // + the byte a matched literal needs
+                const uint32_t off = (uint32_t)((uintptr_t)src & 3u);
+                const uint8_t *a0 = src - off;
+                const uint32_t nch = (off + need + 3) >> 2;      // <= 9
+                LZ_FOR_LANES(l) {
+                    if (l < nch) LZ_CP_ASYNC4(wc.stage + 4 * l, a0 + 4 * l);
+                }
+                LZ_CP_COMMIT();
+                wc.pend_len = len;
+                wc.pend_dst = dst;
+                wc.pend_staged = 1;
+                wc.pend_off = off;
+                wc.pend_dist = dist;
+                d.ctx_a = off + (far ? len - 1 : src_index(len - 1, dist));
+                d.ctx_b = off + (far ? len : src_index(len, dist));
+                d.ctx_pending = 2;
+            } else {
                 if (len <= 32) {
-                    // deferred: load now, store at the next commit
+                    // deferred in registers: load now, store at the next commit
                     LZ_FOR_LANES(l) {
-                        if (l < len) LZ_LV(wc.pend_val, l) = src[l];
+                        if (l < len) LZ_LV(wc.pend_val, l) = src[far ? l : src_index(l, dist)];
                     }
                     wc.pend_len = len;
                     wc.pend_dst = dst;
+                    wc.pend_staged = 0;
                 } else {
                     LZ_FOR_LANES(l) {
-                        for (uint32_t i = l; i < len; i += 32) dst[i] = src[i];
+                        for (uint32_t i = l; i < len; i += 32) dst[i] = src[far ? i : src_index(i, dist)];
                     }
                 }
-                cprev = src + (len - 1);
-                cmatch = src + len;
-            } else {  // the match overlaps itself: period-dist replication (window.go:73-86)
-                if (len <= 32) {
-                    LZ_FOR_LANES(l) {
-                        if (l < len) LZ_LV(wc.pend_val, l) = src[src_index(l, dist)];
-                    }
-                    wc.pend_len = len;
-                    wc.pend_dst = dst;
-                } else {
-                    LZ_FOR_LANES(l) {
-                        for (uint32_t i = l; i < len; i += 32) dst[i] = src[src_index(i, dist)];
-                    }
-                }
-                cprev = src + src_index(len - 1, dist);
-                cmatch = src + src_index(len, dist);
-            }
-            LZ_IF_LANE0 {
                 // context for a literal that may follow: the last byte of the match and the byte at
-                // -(rep0+1) after it.  Both predate the match.  One load site, results untouched
-                // until a literal asks for them.
-                LZ_LD_WIN8(d.ctx_a, cprev);
-                LZ_LD_WIN8(d.ctx_b, cmatch);
+                // -(rep0+1) after it.  One load site, results untouched until a literal asks for them.
+                LZ_LD_WIN8(d.ctx_a, src + (far ? len - 1 : src_index(len - 1, dist)));
+                LZ_LD_WIN8(d.ctx_b, src + (far ? len : src_index(len, dist)));
                 d.ctx_pending = 1;
-                d.outp = dst + len;
             }
+            d.outp = dst + len;
         } else {  // OP_COPY_Q4: dist == bytes since dictionary start + 1; byte "-1" reads as 0
-            LZ_IF_LANE0 {
-                for (uint32_t i = 0; i < len; i++) {
-                    const uint8_t *src = dst + i - dist;
-                    dst[i] = src < dict_base ? (uint8_t)0 : *src;
-                }
-                d.prev_byte = dst[len - 1];
-                const uint8_t *m = dst + len - dist;
-                d.mbyte = m < dict_base ? (uint8_t)0 : *m;
-                d.ctx_pending = 0;
-                d.outp = dst + len;
+            for (uint32_t i = 0; i < len; i++) {   // every lane writes the same bytes
+                const uint8_t *src = dst + i - dist;
+                dst[i] = src < dict_base ? (uint8_t)0 : *src;
             }
+            d.prev_byte = dst[len - 1];
+            const uint8_t *m = dst + len - dist;
+            d.mbyte = m < dict_base ? (uint8_t)0 : *m;
+            d.ctx_pending = 0;
+            d.outp = dst + len;
             LZ_SYNC();
         }
     }
-    LZ_IF_LANE0 {
-        if (fast) d.ip -= 4;   // the word loaded ahead was never consumed
-    }
+    if (fast) d.ip -= 4;   // the word loaded ahead was never consumed
     wc_commit(wc);
 }
 
-// Reload the literal context from memory (window.GetByte(1) / GetByte(rep0+1),
-// decompress.go:50-60) when the decoder (re)starts at a position it did not write.
 template <int kV>
 LZ_DEV void reload_context(Dec &d, const uint8_t *dict_base) {
-    LZ_IF_LANE0 {
-        const uint64_t hist = (uint64_t)(d.outp - dict_base);
-        d.prev_byte = hist > 0 ? d.outp[-1] : 0;
-        d.mbyte = ((uint64_t)d.rep0 + 1 <= hist) ? d.outp[-(int64_t)((uint64_t)d.rep0 + 1)] : 0;
-        d.ctx_pending = 0;
-    }
+    const uint64_t hist = (uint64_t)(d.outp - dict_base);
+    d.prev_byte = hist > 0 ? d.outp[-1] : 0;
+    d.mbyte = ((uint64_t)d.rep0 + 1 <= hist) ? d.outp[-(int64_t)((uint64_t)d.rep0 + 1)] : 0;
+    d.ctx_pending = 0;
 }
 
 struct UnitIO {
@@ -196,6 +192,7 @@ struct UnitIO {
     uint64_t in_len;
     uint8_t *out;            // unit's output
     uint64_t out_cap;
+    uint8_t *stage;          // 64 bytes of shared memory, 4-byte aligned (window-copy staging)
 };
 
 // LZMA1 unit (kind RAW; ALONE units are converted by the host).
@@ -206,6 +203,10 @@ LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     WarpCopy wc;
     wc.pend_len = 0;
     wc.pend_dst = io.out;
+    wc.pend_staged = 0;
+    wc.pend_off = wc.pend_dist = 0;
+    wc.stage = io.stage;
+    wc.out_limit = io.out + io.out_cap;
     set_props(d, u.lc, u.lp, u.pb);
     d.dict_size = u.dict_size;
     d.wpos = 0;
@@ -225,8 +226,7 @@ LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     coder_reset(d, P, L, (uint32_t)u.lc + u.lp);
 
     int32_t r = 0;
-    LZ_IF_LANE0 { r = rc_init(d); }
-    LZ_BCAST32(r);
+    r = rc_init(d);
     if (r < 0) { d.status = LZGPU_UNEXPECTED_EOF; }                       // "rangeDec.Init: %w" of io.EOF
     else if (r > 0) { d.status = LZGPU_RESULT_ERROR; d.site = LZGPU_SITE_RC_INIT; }
     else run_lzma<kV>(d, wc, P, L, io.out);
@@ -248,6 +248,10 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     WarpCopy wc;
     wc.pend_len = 0;
     wc.pend_dst = io.out;
+    wc.pend_staged = 0;
+    wc.pend_off = wc.pend_dist = 0;
+    wc.stage = io.stage;
+    wc.out_limit = io.out + io.out_cap;
     set_props(d, u.lc, u.lp, u.pb);
     d.dict_size = u.dict_size;
     d.wpos = 0;
@@ -283,7 +287,7 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
         // ---- startChunk: lane 0 reads the header, everybody gets the verdict ----
         uint32_t ctrl = 0, hdr = 0;  // hdr: [0]=end [1]=eof ; usz, csz below
         uint32_t usz = 0, csz = 0, newprops = 0xFFFFFFFFu;
-        LZ_IF_LANE0 {
+        {
             const uint64_t rem = (uint64_t)(in_end - ip);
             if (rem == 0) {
                 hdr = 2;  // ran off the unit: fine between units, UnexpectedEOF at the stream's end
@@ -307,7 +311,6 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
                 }
             }
         }
-        LZ_BCAST32(hdr);
         if (hdr != 0) {
             if (hdr == 1) { consumed = (uint64_t)(ip - io.in) + 1; status = LZGPU_OK; }
             else {
@@ -316,10 +319,6 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
             }
             break;
         }
-        LZ_BCAST32(ctrl);
-        LZ_BCAST32(usz);
-        LZ_BCAST32(csz);
-        LZ_BCAST32(newprops);
         const uint32_t hl = ctrl < 0x80 ? 3 : (ctrl < 0xC0 ? 5 : 6);
         const uint8_t *payload = ip + hl;
         if (newprops != 0xFFFFFFFFu) props = newprops;
@@ -383,8 +382,7 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
         d.status = LZGPU_OK;
         d.site = 0;
         int32_t r = 0;
-        LZ_IF_LANE0 { r = rc_init(d); }
-        LZ_BCAST32(r);
+        r = rc_init(d);
         if (r != 0) {
             consumed = (uint64_t)(payload - io.in);
             if (r < 0) { status = LZGPU_UNEXPECTED_EOF; consumed = io.in_len; }
@@ -397,21 +395,12 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
         // what the chunk did, as seen by every lane
         uint32_t st = (uint32_t)d.status, st_site = (uint32_t)d.site, complete = 0, exact = 0;
         uint64_t outbits = 0;
-        LZ_IF_LANE0 {
-            complete = d.outp == d.out_end && d.end_is_size;
-            exact = rc_consumed(d, payload) == (uint64_t)(d.in_end - payload);
-            outbits = (uint64_t)(uintptr_t)d.outp;
-        }
-        LZ_BCAST32(st);
-        LZ_BCAST32(st_site);
-        LZ_BCAST32(complete);
-        LZ_BCAST32(exact);
-        LZ_BCAST64(outbits);
+        complete = d.outp == d.out_end && d.end_is_size;
+        exact = rc_consumed(d, payload) == (uint64_t)(d.in_end - payload);
+        outbits = (uint64_t)(uintptr_t)d.outp;
         d.outp = (uint8_t *)(uintptr_t)outbits;
         // keep the uniform window position in step with lane 0's
         uint32_t wpos = d.wpos, full = d.full;
-        LZ_BCAST32(wpos);
-        LZ_BCAST32(full);
         d.wpos = wpos;
         d.full = full;
 
@@ -442,8 +431,6 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
 
     uint32_t code = d.code;
     uint64_t outbits = (uint64_t)(uintptr_t)d.outp;
-    LZ_BCAST32(code);
-    LZ_BCAST64(outbits);
     LZ_IF_LANE0_ONLY {
         res.status = status;
         res.err_site = site;

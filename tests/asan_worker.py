@@ -32,7 +32,7 @@ for r in range(60):
         i = rng.randrange(13, len(b))
         b[i] ^= 1 << rng.randrange(8)
     cs.append((f"fuzz{r}", bytes(b), rng.choice([len(blk), len(blk) // 2, 3 * len(blk)])))
-for v in (3, 11):
+for v in (0, 1, 17):
     ctx = backends.EmuContext(v)
     for name, st, cap in cs:
         units, in_buf, _, _ = B.build_alone_batch([st], [cap])

@@ -29,7 +29,7 @@ def emu_lib():
 class EmuContext:
     n_devices = 1
 
-    def __init__(self, variant: int = 11):
+    def __init__(self, variant: int = 1):
         self.variant = variant
 
     def decode_batch(self, units, in_buf: np.ndarray, out_buf: np.ndarray):
@@ -62,7 +62,7 @@ class EmuContext:
         pass
 
 
-def make_context(kind: str, variant: int = 11):
+def make_context(kind: str, variant: int = 1):
     if kind == "emu":
         return EmuContext(variant)
     from lzma_b200.batch import Context

@@ -43,11 +43,14 @@ extern "C" int emu_decode_batch(const lzgpu_unit *units, int64_t n, const uint8_
         memset(&r, 0, sizeof r);
         r.status = LZGPU_NOT_RUN;
         uint16_t *P = probs.data(), *L = probs.data() + P_LIT;
+        alignas(16) uint8_t stage[64];
+        io.stage = stage;
         switch (variant) {
-            case 3: run_one<3>(u, io, P, L, bits, r); break;
-            case 11: run_one<11>(u, io, P, L, bits, r); break;
-            case 15: run_one<15>(u, io, P, L, bits, r); break;
-            default: run_one<0>(u, io, P, L, bits, r); break;
+            case 0: run_one<0>(u, io, P, L, bits, r); break;
+            case 5: run_one<5>(u, io, P, L, bits, r); break;
+            case 17: run_one<17>(u, io, P, L, bits, r); break;
+            case 21: run_one<21>(u, io, P, L, bits, r); break;
+            default: run_one<1>(u, io, P, L, bits, r); break;
         }
         if (alone) r.bytes_in += 13;
         r.device = -1;
