@@ -121,6 +121,10 @@ struct Dec {
     uint32_t ctx_pending;           // 1 = values loaded into ctx_a/b, 2 = offsets into `stage` (cp.async)
     const uint8_t *stage;           // V_STAGE: the warp's shared staging buffer for window-copy sources
     int32_t status, site;
+    // V_CHAIN fast decoder (lzgpu_fast2.cuh): compressed input staged in shared memory, read a byte ahead
+    uint32_t nb, ips, lims;         // next input byte (already loaded); its shared address; last address a symbol may start at
+    uint32_t sP, sL, sIn;           // shared-window addresses of the fixed tables, the literal tables, the input stage
+    const uint8_t *g0;              // global address of the byte staged at sIn
 };
 
 // Input is consumed through a 64-bit lookahead register so that the per-bit
@@ -180,7 +184,15 @@ LZ_HD void rc_fill(Dec &d) {
 //   V_STAGE     window-copy sources are staged in shared memory by cp.async instead of being held
 //               in registers until the deferred store: no load result is outstanding when the
 //               decoder resumes, so nothing in it can be made to wait on the window
-enum : int { V_FAST = 1, V_PREFETCH = 4, V_STAGE = 16 };
+//   V_CHAIN     the fast decoder is the one in lzgpu_fast2.cuh (latency-optimised dependency chain: both
+//               children of a tree node are loaded before the bit is known, every conditional update is
+//               one predicated instruction, compressed input is staged in shared memory and read one
+//               byte ahead so that there are no lookahead top-ups).  Literal tables use the layout
+//               described there (also by the careful decoder of the same instantiation).
+enum : int { V_FAST = 1, V_PREFETCH = 4, V_STAGE = 16, V_CHAIN = 32 };
+constexpr uint32_t kF2Stage = 512;        // bytes of compressed input staged per refill (V_CHAIN)
+constexpr uint32_t kF2Margin = 41;        // a symbol consumes <= 21 bytes; the byte-ahead read adds 1
+constexpr uint32_t kF2MinInput = 128;     // do not (re)enter the V_CHAIN fast decoder with less input left
 constexpr uint32_t kFastInMargin = 64;    // >= 48 bit steps of one symbol + one word loaded ahead + slack
 constexpr uint32_t kFastOutMargin = 274;  // longest match is 273
 
@@ -230,7 +242,16 @@ LZ_HD uint64_t rc_consumed(const Dec &d, const uint8_t *start) {
 
 // May the fast decoder start a symbol here?  (ip is where the careful decoder loads next;
 // the fast one keeps one more word loaded ahead, hence the +4.)
+template <int kV>
 LZ_HD bool fast_possible(const Dec &d) {
+    if (kV & V_CHAIN) {
+#if defined(__CUDA_ARCH__)
+        // all buffered bytes are real (phantom == 0); the next unconsumed byte is at ip - inbits/8
+        return d.phantom == 0 && (uint64_t)(d.in_end - d.ip) + (d.inbits >> 3) >= kF2MinInput && d.outp <= d.fast_out_end;
+#else
+        return false;   // host lane emulation: the careful decoder runs everything (same table layout)
+#endif
+    }
     return ((uintptr_t)d.ip & 3u) == 0 && d.phantom == 0 && d.ip + 4 <= d.fast_in_end && d.outp <= d.fast_out_end;
 }
 LZ_HD void set_fast_limits(Dec &d) {
@@ -463,7 +484,7 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
         // careful decoder: hand over as soon as the fast one may run
         if (kFast) {
             if (LZ_UNLIKELY(d.ip > d.fast_in_end || d.outp > d.fast_out_end)) return OP_SWITCH;
-        } else if ((kV & V_FAST) && fast_possible(d)) {
+        } else if ((kV & V_FAST) && fast_possible<kV>(d)) {
             return OP_SWITCH;
         }
         const bool at_end = !kFast && (d.outp == d.out_end);
@@ -502,6 +523,19 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
             // :59-114) and drops to 0 at the first mismatch, after which the index is the
             // plain one (:127-166).  Index = offs + match_bit + sym = ((1 + matchBit) << 8) + sym.
             uint32_t sym = 1;
+            if (kV & V_CHAIN) {
+                // V_CHAIN table layout: plain node m at [m]; matched node at [0x100 + 2m + matchBit]
+                // (the reference's is [((1 + matchBit) << 8) + m]; a private permutation of the same cells)
+                uint32_t matched = d.state >= 7 ? 1u : 0u;
+#pragma unroll 1
+                for (int i = 0; i < 8; i++) {
+                    if (i == 4) LZ_FILL();
+                    const uint32_t mbit = (matchb >> (7 - i)) & 1u;
+                    LZ_BIT(pr + (matched ? 0x100u + 2u * sym + mbit : sym), bit);
+                    sym = (sym << 1) | bit;
+                    matched &= (bit == mbit) ? 1u : 0u;
+                }
+            } else {
             uint32_t offs = d.state >= 7 ? 0x100u : 0u;
             uint32_t mb = matchb;
 #pragma unroll
@@ -512,6 +546,7 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
                 offs &= mb;                                      // match bit, if still in matched mode
                 LZ_BIT_MLIT(pr + offs + old + sym, bit, offs, old);   // offs stays set only while bit == match bit
                 sym = (sym << 1) | bit;
+            }
             }
             if (LZ_UNLIKELY(LZ_EXHAUSTED())) goto input_eof;
             sym &= 0xFF;

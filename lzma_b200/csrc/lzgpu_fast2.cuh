@@ -1,0 +1,433 @@
+// lzgpu_fast2.cuh -- the V_CHAIN fast decoder: the same symbol loop as decode_run<kV, true>
+// (lzgpu_core.cuh; reference decompress.go:8-1136), rebuilt around the LATENCY of the serial
+// dependency chain, because that -- not bandwidth, not occupancy -- bounds a unit.
+//
+// What the ncu source view of the previous fast decoder showed (profiles/r01_final_*): one adaptive
+// bit took ~55-60 cycles for a lone warp although its range arithmetic needs ~24, because the chain
+//     bit -> tree index -> address (4 ALU ops) -> LDS (~30 cycles) -> multiply -> compare -> bit
+// sits on the critical path.  Here
+//   * bit trees keep the address of the CHILDREN PAIR of the current node (y = base + 4m) and load both
+//     children before the bit is known; the decided bit then costs one select (value) and one
+//     predicated add (next pair address) -- the loads have a whole step to arrive;
+//   * matched literals (decompress.go:59-114) walk a path that is known from the match byte alone, so
+//     the probability of the next matched node and of the plain node a mismatch would lead to are
+//     both loaded ahead, from addresses computed off the critical path; a mismatch branches into the
+//     plain ladder at the same depth (one uniform branch per literal);
+//   * the probability store needs no address arithmetic (two predicated stores off the pair address);
+//   * compressed input is staged in shared memory (512 B per refill) and consumed through a
+//     byte-ahead register: a normalisation is five predicated instructions and there are no
+//     lookahead top-ups at all (the previous decoder spent ~1.8 instructions per bit on them);
+//   * single bits (isMatch, isRep, ...) get their probability loaded before the preceding step.
+//
+// Literal-table layout of this variant (private; every cell still starts at 1024, state.go:79-121):
+// per context 0x300 cells; plain tree node m (1..255) at cell m; matched node for (prefix m, match
+// bit b) at cell 0x100 + 2m + b.  The careful decoder of the same instantiation uses the same cells.
+//
+// Device only: the host lane emulation (tests/emu) runs the careful decoder for this variant.
+#pragma once
+#include "lzgpu_core.cuh"
+
+namespace lzgpu {
+
+#if defined(__CUDA_ARCH__)
+
+// ---- PTX building blocks.  Operand convention of every block:
+//   %0 range  %1 code  %2 nb (next input byte)  %3 ips (shared address of that byte)   -- all "+r"
+//   %4 the block's result, %5.. its inputs.
+#define F2_REGS                                                                         \
+    ".reg .pred one, nz, q0, q1, mbp, ne;\n\t"                                          \
+    ".reg .b32 t, bd, k, pn, p, lo, hi, ya, yb, yc, nS;\n\t"
+
+// DecodeBit arithmetic (range_decoder.go:57-98) on probability register P; predicate Q = the bit.
+#define F2_CORE(P, Q)                                                                   \
+    "shr.u32 t, %0, 11;\n\t"                                                            \
+    "mul.lo.u32 bd, t, " P ";\n\t"                                                      \
+    "sub.s32 k, 31, " P ";\n\t"                                                         \
+    "setp.ge.u32 " Q ", %1, bd;\n\t"                                                    \
+    "sub.u32 t, %0, bd;\n\t"                                                            \
+    "selp.b32 %0, t, bd, " Q ";\n\t"                                                    \
+    "@" Q " sub.u32 %1, %1, bd;\n\t"
+// pn = P + ((Q ? 31 : 2048) - P) >> 5   (p - (p >> 5) for a 1, p + ((2048 - p) >> 5) for a 0)
+#define F2_UPD(P, Q)                                                                    \
+    "@!" Q " sub.s32 k, 2048, " P ";\n\t"                                               \
+    "shr.s32 k, k, 5;\n\t"                                                              \
+    "add.s32 pn, " P ", k;\n\t"
+// normalisation: consume the byte in hand, fetch the one after it
+#define F2_NORM                                                                         \
+    "setp.lt.u32 nz, %0, 0x1000000;\n\t"                                                \
+    "@nz shl.b32 %0, %0, 8;\n\t"                                                        \
+    "@nz mad.lo.u32 %1, %1, 256, %2;\n\t"                                               \
+    "@nz ld.shared.u8 %2, [%3+1];\n\t"                                                  \
+    "@nz add.u32 %3, %3, 1;\n\t"
+
+#define F2_LD(Y) "ld.shared.u16 lo, [" Y "];\n\tld.shared.u16 hi, [" Y "+2];\n\t"
+#define F2_NOLD(Y) ""
+// One level of a heap-ordered bit tree.  On entry: p = probability of the current node, lo / hi =
+// its children's, loaded from [YC] / [YC+2] (YC = base + 4m).  The node itself lives at YP + (QP ? 2 : 0).
+// On exit YN = pair address of the chosen child's children (loaded if LOADS), p = the chosen child's.
+#define F2_STEP(YP, QP, YC, YN, QC, NS, LOADS)                                          \
+    F2_CORE("p", QC)                                                                    \
+    "mad.lo.u32 " YN ", " YC ", 2, " NS ";\n\t"                                         \
+    "@" QC " add.u32 " YN ", " YN ", 4;\n\t"                                            \
+    F2_UPD("p", QC)                                                                     \
+    "selp.b32 p, hi, lo, " QC ";\n\t"                                                   \
+    LOADS(YN)                                                                           \
+    "@" QP " st.shared.u16 [" YP "+2], pn;\n\t"                                         \
+    "@!" QP " st.shared.u16 [" YP "], pn;\n\t"                                          \
+    F2_NORM
+// the root level: node at [BASE+2]
+#define F2_STEP0(BASE, YC, YN, QC, NS, LOADS)                                           \
+    F2_CORE("p", QC)                                                                    \
+    "mad.lo.u32 " YN ", " YC ", 2, " NS ";\n\t"                                         \
+    "@" QC " add.u32 " YN ", " YN ", 4;\n\t"                                            \
+    F2_UPD("p", QC)                                                                     \
+    "selp.b32 p, hi, lo, " QC ";\n\t"                                                   \
+    LOADS(YN)                                                                           \
+    "st.shared.u16 [" BASE "+2], pn;\n\t"                                               \
+    F2_NORM
+// levels by depth; the pair-address registers rotate yb -> yc -> ya, the predicates alternate
+#define F2_L0(BASE, LOADS) F2_STEP0(BASE, "yb", "yc", "q0", "nS", LOADS)
+#define F2_L1(LOADS) F2_STEP("yb", "q0", "yc", "ya", "q1", "nS", LOADS)
+#define F2_L2(LOADS) F2_STEP("yc", "q1", "ya", "yb", "q0", "nS", LOADS)
+#define F2_L3(LOADS) F2_STEP("ya", "q0", "yb", "yc", "q1", "nS", LOADS)
+#define F2_L4(LOADS) F2_STEP("yb", "q1", "yc", "ya", "q0", "nS", LOADS)
+#define F2_L5(LOADS) F2_STEP("yc", "q0", "ya", "yb", "q1", "nS", LOADS)
+#define F2_L6(LOADS) F2_STEP("ya", "q1", "yb", "yc", "q0", "nS", LOADS)
+#define F2_L7(LOADS) F2_STEP("yb", "q0", "yc", "ya", "q1", "nS", LOADS)
+// pair address after n levels: n=3 -> yb, 4 -> yc, 6 -> yb, 8 -> ya; node index m = (y - base) >> 2
+#define F2_ROOT(BASE)                                                                   \
+    "neg.s32 nS, " BASE ";\n\t"                                                         \
+    "ld.shared.u16 p, [" BASE "+2];\n\t"                                                \
+    "ld.shared.u16 lo, [" BASE "+4];\n\t"                                               \
+    "ld.shared.u16 hi, [" BASE "+6];\n\t"                                               \
+    "add.u32 yb, " BASE ", 4;\n\t"
+
+#define F2_IO(d) "+r"((d).range), "+r"((d).code), "+r"((d).nb), "+r"((d).ips)
+
+__device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+
+// one adaptive bit whose probability PV was loaded from shared address A earlier
+#define F2_BIT(d, PV, A, BIT)                                                           \
+    asm volatile("{\n\t" F2_REGS                                                        \
+                 F2_CORE("%6", "one") F2_UPD("%6", "one")                               \
+                 "st.shared.u16 [%5], pn;\n\t"                                          \
+                 "selp.u32 %4, 1, 0, one;\n\t"                                          \
+                 F2_NORM "}"                                                            \
+                 : F2_IO(d), "=&r"(BIT) : "r"(A), "r"(PV) : "memory")
+
+// 6-level tree at byte address BASE (posSlot, decompress.go:441-486): result = node index 64..127
+#define F2_TREE6(d, OUT, BASE)                                                          \
+    asm volatile("{\n\t" F2_REGS F2_ROOT("%5")                                          \
+                 F2_L0("%5", F2_LD) F2_L1(F2_LD) F2_L2(F2_LD) F2_L3(F2_LD) F2_L4(F2_LD) F2_L5(F2_NOLD) \
+                 "add.u32 t, yb, nS;\n\tshr.u32 %4, t, 2;\n\t}"                          \
+                 : F2_IO(d), "=&r"(OUT) : "r"(BASE) : "memory")
+// 4-level tree (align, decompress.go:580-625, LSB first): result = node index 16..31, bits MSB-first
+#define F2_TREE4(d, OUT, BASE)                                                          \
+    asm volatile("{\n\t" F2_REGS F2_ROOT("%5")                                          \
+                 F2_L0("%5", F2_LD) F2_L1(F2_LD) F2_L2(F2_LD) F2_L3(F2_NOLD)            \
+                 "add.u32 t, yc, nS;\n\tshr.u32 %4, t, 2;\n\t}"                          \
+                 : F2_IO(d), "=&r"(OUT) : "r"(BASE) : "memory")
+
+// lenDecoder.Decode (len_decoder.go:34-60; live copies decompress.go:218-429, 870-1118).
+// SLEN = byte address of the coder, SLOW = byte address of its low tree for this posState
+// (mid tree = SLOW + 256, high tree = SLEN + 528).  Result 0..271.
+#define F2_LEN(d, OUT, SLEN, SLOW)                                                      \
+    asm volatile("{\n\t" F2_REGS ".reg .b32 bs, pc2, pr0;\n\t"                          \
+                 "ld.shared.u16 p, [%5];\n\t"                                           \
+                 "ld.shared.u16 pc2, [%5+2];\n\t"                                       \
+                 "ld.shared.u16 pr0, [%6+2];\n\t"                                       \
+                 "ld.shared.u16 lo, [%6+4];\n\t"                                        \
+                 "ld.shared.u16 hi, [%6+6];\n\t"                                        \
+                 F2_CORE("p", "one") F2_UPD("p", "one")                                 \
+                 "st.shared.u16 [%5], pn;\n\t"                                          \
+                 F2_NORM                                                                \
+                 "@one bra.uni F2_LEN_CH2;\n\t"                                         \
+                 "mov.b32 bs, %6;\n\t"                                                  \
+                 "mov.b32 p, pr0;\n\t"                                                  \
+                 "mov.u32 %4, 0xfffffff8;\n\t"                                          \
+                 "bra.uni F2_LEN_T3;\n\t"                                               \
+                 "F2_LEN_CH2:\n\t"                                                      \
+                 "add.u32 bs, %6, 256;\n\t"                                             \
+                 "ld.shared.u16 pr0, [bs+2];\n\t"                                       \
+                 "ld.shared.u16 lo, [bs+4];\n\t"                                        \
+                 "ld.shared.u16 hi, [bs+6];\n\t"                                        \
+                 F2_CORE("pc2", "one") F2_UPD("pc2", "one")                             \
+                 "st.shared.u16 [%5+2], pn;\n\t"                                        \
+                 F2_NORM                                                                \
+                 "@one bra.uni F2_LEN_HI;\n\t"                                          \
+                 "mov.b32 p, pr0;\n\t"                                                  \
+                 "mov.u32 %4, 0;\n\t"                                                   \
+                 "F2_LEN_T3:\n\t"                                                       \
+                 "neg.s32 nS, bs;\n\t"                                                  \
+                 "add.u32 yb, bs, 4;\n\t"                                               \
+                 F2_L0("bs", F2_LD) F2_L1(F2_LD) F2_L2(F2_NOLD)                         \
+                 "add.u32 t, yb, nS;\n\t"                                               \
+                 "shr.u32 t, t, 2;\n\t"                                                 \
+                 "add.u32 %4, %4, t;\n\t"                                               \
+                 "bra.uni F2_LEN_END;\n\t"                                              \
+                 "F2_LEN_HI:\n\t"                                                       \
+                 "add.u32 bs, %5, 528;\n\t"                                             \
+                 F2_ROOT("bs")                                                          \
+                 F2_L0("bs", F2_LD) F2_L1(F2_LD) F2_L2(F2_LD) F2_L3(F2_LD) F2_L4(F2_LD) F2_L5(F2_LD) F2_L6(F2_LD) F2_L7(F2_NOLD) \
+                 "add.u32 t, ya, nS;\n\t"                                               \
+                 "shr.u32 t, t, 2;\n\t"                                                 \
+                 "add.u32 %4, t, 0xffffff10;\n\t"                                       \
+                 "F2_LEN_END:\n\t}"                                                     \
+                 : F2_IO(d), "=&r"(OUT) : "r"(SLEN), "r"(SLOW) : "memory")
+
+// ---- literal (decompress.go:49-169).  %5 = byte address S of the context's 0x300 cells,
+// %6 = 0x100 | match byte, %7 != 0: matched mode (state >= 7).  Result = the byte.
+// Matched level i: x = (0x100 | mb) >> (7 - i) = 2 * prefix + match bit; u = S + 2x; its cell is [u + 512];
+// the plain node a mismatch leads to is x ^ 1 = cell [u ^ 2] (S is 4-byte aligned).
+#define F2_MLEVEL(X, U, PC, XN, UN, PNX, SHN, MIS)                                      \
+    "shr.u32 " XN ", %6, " SHN ";\n\t"                                                  \
+    "mad.lo.u32 " UN ", " XN ", 2, %5;\n\t"                                             \
+    "ld.shared.u16 " PNX ", [" UN "+512];\n\t"                                          \
+    "xor.b32 v, " U ", 2;\n\t"                                                          \
+    "ld.shared.u16 pmis, [v];\n\t"                                                      \
+    "and.b32 t, " X ", 1;\n\t"                                                          \
+    "setp.ne.u32 mbp, t, 0;\n\t"                                                        \
+    F2_CORE(PC, "one") F2_UPD(PC, "one")                                                \
+    "st.shared.u16 [" U "+512], pn;\n\t"                                                \
+    "xor.pred ne, one, mbp;\n\t"                                                        \
+    F2_NORM                                                                             \
+    "@ne bra.uni " MIS ";\n\t"
+// mismatch at level i: enter plain level i+1 at node v (YP / QP / YC are that level's names)
+#define F2_MIS(LABEL, YP, QP, YC, TARGET)                                               \
+    LABEL ":\n\t"                                                                       \
+    "mov.b32 p, pmis;\n\t"                                                              \
+    "mov.b32 " YP ", v;\n\t"                                                            \
+    "setp.lt.u32 " QP ", %5, 0;\n\t"                                                    \
+    "mad.lo.u32 " YC ", v, 2, nS;\n\t"                                                  \
+    F2_LD(YC)                                                                           \
+    "bra.uni " TARGET ";\n\t"
+
+#define F2_LIT(d, OUT, S, MB, MATCHED)                                                  \
+    asm volatile("{\n\t" F2_REGS ".reg .b32 xa, xb, ua, ub, pa, pb, v, pmis;\n\t"       \
+                 "neg.s32 nS, %5;\n\t"                                                  \
+                 "setp.ne.u32 one, %7, 0;\n\t"                                          \
+                 "@one bra.uni F2_LIT_M;\n\t"                                           \
+                 "ld.shared.u16 p, [%5+2];\n\t"                                         \
+                 "ld.shared.u16 lo, [%5+4];\n\t"                                        \
+                 "ld.shared.u16 hi, [%5+6];\n\t"                                        \
+                 "add.u32 yb, %5, 4;\n\t"                                               \
+                 F2_L0("%5", F2_LD)                                                     \
+                 "F2_PL1:\n\t" F2_L1(F2_LD)                                             \
+                 "F2_PL2:\n\t" F2_L2(F2_LD)                                             \
+                 "F2_PL3:\n\t" F2_L3(F2_LD)                                             \
+                 "F2_PL4:\n\t" F2_L4(F2_LD)                                             \
+                 "F2_PL5:\n\t" F2_L5(F2_LD)                                             \
+                 "F2_PL6:\n\t" F2_L6(F2_LD)                                             \
+                 "F2_PL7:\n\t" F2_L7(F2_NOLD)                                           \
+                 "add.u32 t, ya, nS;\n\t"                                               \
+                 "shr.u32 t, t, 2;\n\t"                                                 \
+                 "and.b32 %4, t, 255;\n\t"                                              \
+                 "bra.uni F2_LIT_END;\n\t"                                              \
+                 "F2_LIT_M:\n\t"                                                        \
+                 "shr.u32 xa, %6, 7;\n\t"                                               \
+                 "mad.lo.u32 ua, xa, 2, %5;\n\t"                                        \
+                 "ld.shared.u16 pa, [ua+512];\n\t"                                      \
+                 F2_MLEVEL("xa", "ua", "pa", "xb", "ub", "pb", "6", "F2_MIS0")          \
+                 F2_MLEVEL("xb", "ub", "pb", "xa", "ua", "pa", "5", "F2_MIS1")          \
+                 F2_MLEVEL("xa", "ua", "pa", "xb", "ub", "pb", "4", "F2_MIS2")          \
+                 F2_MLEVEL("xb", "ub", "pb", "xa", "ua", "pa", "3", "F2_MIS3")          \
+                 F2_MLEVEL("xa", "ua", "pa", "xb", "ub", "pb", "2", "F2_MIS4")          \
+                 F2_MLEVEL("xb", "ub", "pb", "xa", "ua", "pa", "1", "F2_MIS5")          \
+                 F2_MLEVEL("xa", "ua", "pa", "xb", "ub", "pb", "0", "F2_MIS6")          \
+                 /* level 7: x = 0x100 | mb in xb; the byte is its prefix with the decoded bit */ \
+                 F2_CORE("pb", "one") F2_UPD("pb", "one")                               \
+                 "st.shared.u16 [ub+512], pn;\n\t"                                      \
+                 F2_NORM                                                                \
+                 "and.b32 t, xb, 254;\n\t"                                              \
+                 "selp.u32 k, 1, 0, one;\n\t"                                           \
+                 "or.b32 %4, t, k;\n\t"                                                 \
+                 "bra.uni F2_LIT_END;\n\t"                                              \
+                 F2_MIS("F2_MIS0", "yb", "q0", "yc", "F2_PL1")                          \
+                 F2_MIS("F2_MIS1", "yc", "q1", "ya", "F2_PL2")                          \
+                 F2_MIS("F2_MIS2", "ya", "q0", "yb", "F2_PL3")                          \
+                 F2_MIS("F2_MIS3", "yb", "q1", "yc", "F2_PL4")                          \
+                 F2_MIS("F2_MIS4", "yc", "q0", "ya", "F2_PL5")                          \
+                 F2_MIS("F2_MIS5", "ya", "q1", "yb", "F2_PL6")                          \
+                 F2_MIS("F2_MIS6", "yb", "q0", "yc", "F2_PL7")                          \
+                 "F2_LIT_END:\n\t}"                                                     \
+                 : F2_IO(d), "=&r"(OUT) : "r"(S), "r"(MB), "r"(MATCHED) : "memory")
+
+// consume one input byte outside an adaptive step (direct bits, decompress.go:549-576)
+#define F2_SHIFT8(d)                                                                    \
+    asm volatile("shl.b32 %0, %0, 8;\n\t"                                               \
+                 "mad.lo.u32 %1, %1, 256, %2;\n\t"                                      \
+                 "ld.shared.u8 %2, [%3+1];\n\t"                                         \
+                 "add.u32 %3, %3, 1;"                                                   \
+                 : F2_IO(d) : : "memory")
+
+#define F2_FAIL(ST, SITE) do { d.status = (ST); d.site = (SITE); return OP_DONE; } while (0)
+
+// Same contract as decode_run<kV, true>: runs until a symbol needs the warp (OP_COPY / OP_COPY_Q4 with
+// len and dist set), the unit part ends (OP_DONE) or the staged input / the output margin is used up
+// (OP_SWITCH: the caller refills the stage or hands over to the careful decoder).
+template <int kV>
+__device__ __forceinline__ uint32_t decode_fast2(Dec &d, uint32_t &out_len, uint32_t &out_dist) {
+    const uint32_t sP = d.sP;
+    for (;;) {
+        if (LZ_UNLIKELY(d.ips > d.lims || d.outp > d.fast_out_end)) return OP_SWITCH;
+
+        const uint32_t pos_state = d.wpos & d.pos_mask;          // decompress.go:22
+        const uint32_t state2 = (d.state << 4) + pos_state;      // :23
+        const uint32_t a_im = sP + 2u * P_IS_MATCH + 2u * state2;
+        const uint32_t a_rep = sP + 2u * P_REP4 + 8u * d.state;
+        const uint32_t p_im = f2_lds16(a_im);
+        const uint32_t p_rep = f2_lds16(a_rep);                  // in flight while isMatch decodes
+        uint32_t bit;
+        F2_BIT(d, p_im, a_im, bit);                              // :25-42
+
+        if (bit == 0) {  // literal, :44-175
+            uint32_t prevb = d.prev_byte, matchb = d.mbyte;
+            if (d.ctx_pending) {                                 // first use of the last window copy's context loads
+                prevb = d.ctx_a;
+                matchb = d.ctx_b;
+            }
+            d.ctx_pending = 0;
+            const uint32_t S = d.sL + 0x600u * (((d.wpos & d.lp_mask) << d.lc) + (prevb >> (8 - d.lc)));  // :56-57
+            uint32_t sym;
+            F2_LIT(d, sym, S, 0x100u | matchb, d.state >= 7 ? 1u : 0u);
+            *d.outp++ = (uint8_t)sym;                             // PutByte, :168
+            d.prev_byte = sym;
+            d.wpos++;
+            if (LZ_UNLIKELY(d.wpos >= d.dict_size)) { d.wpos -= d.dict_size; d.full = 1; }
+            d.state = d.state < 4 ? 0 : (d.state < 10 ? d.state - 3 : d.state - 6);  // stateUpdateLiteral
+            continue;
+        }
+
+        uint32_t len;
+        F2_BIT(d, p_rep, a_rep, bit);                             // isRep, :195-213
+        if (bit == 0) {  // simple match, :215-668
+            d.rep3 = d.rep2; d.rep2 = d.rep1; d.rep1 = d.rep0;    // :216
+            F2_LEN(d, len, sP + 2u * P_LEN0, sP + 2u * (P_LEN0 + LEN_LOW) + 16u * pos_state);   // :218-429
+            d.state = d.state < 7 ? 7 : 10;                       // stateUpdateMatch, :431
+            const uint32_t len_state = len > 3 ? 3 : len;         // :434-437
+            uint32_t slot;
+            F2_TREE6(d, slot, sP + 2u * P_POS_SLOT + (len_state << 7));   // :441-486
+            slot -= 64;
+            if (LZ_UNLIKELY(slot < 4)) {
+                d.rep0 = slot;                                    // :488-489
+            } else {
+                const uint32_t nd = (slot >> 1) - 1;
+                uint32_t dist = (2 | (slot & 1)) << nd, v;
+                if (LZ_UNLIKELY(slot < 14)) {                     // :494-546, LSB first
+                    const uint32_t tb = sP + 2u * (P_POS_DEC + dist - 4);   // own sub-table layout (lzgpu_core.cuh)
+                    uint32_t m = 1;
+                    v = 0;
+#pragma unroll 1
+                    for (uint32_t i = 0; i < nd; i++) {
+                        const uint32_t a = tb + 2u * m;
+                        const uint32_t pv = f2_lds16(a);
+                        F2_BIT(d, pv, a, bit);
+                        m = (m << 1) | bit;
+                        v |= bit << i;
+                    }
+                    dist += v;
+                } else {                                          // :548-628
+                    // DecodeDirectBits: as in decode_run (runs of halvings between normalisations)
+                    uint32_t res = 0;
+                    uint32_t n = nd - 4;                           // 1..26
+                    uint32_t g = 8 - LZ_CLZ(d.range);
+#pragma unroll 1
+                    for (;;) {
+                        const uint32_t k = n < g ? n : g;
+                        const uint32_t r0 = d.range;
+                        uint32_t acc = 0;
+#pragma unroll
+                        for (uint32_t j = 1; j <= 8; j++) {
+                            asm("{\n\t.reg .pred live, one;\n\t.reg .b32 rj;\n\t"
+                                "setp.le.u32 live, %3, %4;\n\t"
+                                "shr.u32 rj, %2, %3;\n\t"
+                                "setp.ge.and.u32 one, %0, rj, live;\n\t"
+                                "@one sub.u32 %0, %0, rj;\n\t"
+                                "@one or.b32 %1, %1, %5;\n\t}"
+                                : "+r"(d.code), "+r"(acc)
+                                : "r"(r0), "r"(j), "r"(k), "r"(1u << (8 - j)));
+                        }
+                        d.range = r0 >> k;
+                        res = (res << k) | (acc >> (8 - k));
+                        n -= k;
+                        if (k == g) F2_SHIFT8(d);
+                        g = 8;
+                        if (n == 0) break;
+                    }
+                    dist += res << 4;
+                    uint32_t m;
+                    F2_TREE4(d, m, sP + 2u * P_ALIGN);            // :580-625
+                    dist += __brev(m) >> 28;
+                }
+                d.rep0 = dist;
+            }
+            if (LZ_UNLIKELY(d.rep0 == 0xFFFFFFFFu)) {             // EOS marker, :633-645 (never at the declared end here)
+                if (d.code == 0) {
+                    if (d.size_defined) F2_FAIL(LZGPU_RESULT_ERROR, 636);
+                    F2_FAIL(LZGPU_OK, 0);
+                }
+                F2_FAIL(LZGPU_RESULT_ERROR, 643);
+            }
+            if (LZ_UNLIKELY(d.rep0 >= d.dict_size || !(d.full || d.rep0 <= d.wpos)))  // :651-653 (Q4 as written)
+                F2_FAIL(LZGPU_RESULT_ERROR, 652);
+            len += 2;                                             // :656
+        } else {  // rep match, :685-1118
+            if (LZ_UNLIKELY(d.wpos == 0 && !d.full)) F2_FAIL(LZGPU_RESULT_ERROR, 691);  // IsEmpty, :690-692
+            bool short_rep = false;
+            uint32_t a = a_rep + 2, pv = f2_lds16(a);
+            F2_BIT(d, pv, a, bit);                                // isRepG0, :694-772
+            if (bit == 0) {
+                a = sP + 2u * P_IS_REP0_LONG + 2u * state2;
+                pv = f2_lds16(a);
+                F2_BIT(d, pv, a, bit);                            // :715-755
+                short_rep = (bit == 0);
+            } else {
+                uint32_t dist;
+                a = a_rep + 4;
+                pv = f2_lds16(a);
+                F2_BIT(d, pv, a, bit);                            // isRepG1, :777-813
+                if (bit == 0) {
+                    dist = d.rep1; d.rep1 = d.rep0; d.rep0 = dist;
+                } else {
+                    a = a_rep + 6;
+                    pv = f2_lds16(a);
+                    F2_BIT(d, pv, a, bit);                        // isRepG2, :816-861
+                    if (bit == 0) { dist = d.rep2; d.rep2 = d.rep1; d.rep1 = d.rep0; d.rep0 = dist; }
+                    else { dist = d.rep3; d.rep3 = d.rep2; d.rep2 = d.rep1; d.rep1 = d.rep0; d.rep0 = dist; }
+                }
+            }
+            if (short_rep) {                                      // :735-739
+                d.state = d.state < 7 ? 9 : 11;                   // stateUpdateShortRep
+                len = 1;
+            } else {
+                F2_LEN(d, len, sP + 2u * P_LEN1, sP + 2u * (P_LEN1 + LEN_LOW) + 16u * pos_state);   // :870-1101
+                d.state = d.state < 7 ? 8 : 11;                   // stateUpdateRep
+                len += 2;
+            }
+        }
+
+        // copy: decompress.go:656-668 / :934-947 / :1028-1041 / :1104-1117 (sizes cannot be exceeded here)
+        const uint32_t dist = d.rep0 + 1;
+        uint32_t op = OP_COPY;
+        if (LZ_UNLIKELY(!d.full && dist > d.wpos)) {
+            if (dist != d.wpos + 1) F2_FAIL(LZGPU_RESULT_ERROR, LZGPU_SITE_REP_BEFORE_DICT);   // Q5
+            op = OP_COPY_Q4;                                      // Q4
+        }
+        d.wpos += len;
+        if (LZ_UNLIKELY(d.wpos >= d.dict_size)) { d.wpos -= d.dict_size; d.full = 1; }
+        out_len = len;
+        out_dist = dist;
+        return op;
+    }
+}
+
+#else   // host passes: never called (fast_possible<V_CHAIN> is false off the device)
+template <int kV>
+LZ_HD uint32_t decode_fast2(Dec &, uint32_t &, uint32_t &) { return OP_DONE; }
+#endif
+
+}  // namespace lzgpu

@@ -15,6 +15,7 @@
 // uncompressedRead (reader2.go:100-294) for LZMA2 groups.
 #pragma once
 #include "lzgpu_core.cuh"
+#include "lzgpu_fast2.cuh"
 
 #if defined(__CUDA_ARCH__)
 #define LZ_LANE() (threadIdx.x & 31u)
@@ -82,22 +83,86 @@ LZ_DEV void coder_reset(Dec &d, uint16_t *P, uint16_t *L, uint32_t lit_bits) {
     LZ_SYNC();
 }
 
+// V_CHAIN addresses its tables and the input stage through 32-bit shared-window addresses
+LZ_DEV void set_shared_addrs(Dec &d, uint16_t *P, uint8_t *inbuf) {
+#if defined(__CUDA_ARCH__)
+    d.sP = (uint32_t)__cvta_generic_to_shared(P);
+    d.sL = d.sP + 2u * P_LIT;
+    d.sIn = (uint32_t)__cvta_generic_to_shared(inbuf);
+#else
+    d.sP = d.sL = d.sIn = 0;
+#endif
+    d.nb = d.ips = d.lims = 0;
+    d.g0 = nullptr;
+}
+
 LZ_DEV void set_props(Dec &d, uint32_t lc, uint32_t lp, uint32_t pb) {
     d.lc = lc;
     d.lp_mask = (1u << lp) - 1;
     d.pos_mask = (1u << pb) - 1;
 }
 
+// V_CHAIN: (re)fill the shared input stage from the next unconsumed byte `gpos` and point the byte-ahead
+// register at it.  False when too little input is left for the fast decoder to be worth entering.
+template <int kV>
+LZ_DEV bool f2_enter(Dec &d, const uint8_t *gpos, uint8_t *inbuf) {
+#if defined(__CUDA_ARCH__)
+    if ((uint64_t)(d.in_end - gpos) < kF2MinInput) return false;
+    const uint8_t *g0 = (const uint8_t *)((uintptr_t)gpos & ~(uintptr_t)15);
+    const uint64_t span = (uint64_t)(d.in_end - g0);
+    const uint32_t avail = span >= kF2Stage ? kF2Stage : ((uint32_t)span & ~15u);   // whole 16-byte chunks of this unit only
+    const uint32_t l = LZ_LANE();
+    if (16u * l + 16u <= avail) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(g0) + l);
+        reinterpret_cast<uint4 *>(inbuf)[l] = w;
+    }
+    if (l < 4 && g0 + kF2Stage + 128u * l < d.in_end) LZ_PREFETCH_L2(g0 + kF2Stage + 128u * l);
+    __syncwarp();
+    const uint32_t off = (uint32_t)(gpos - g0);
+    d.g0 = g0;
+    d.ips = d.sIn + off;
+    d.lims = d.sIn + avail - kF2Margin;
+    d.nb = inbuf[off];
+    return true;
+#else
+    return false;
+#endif
+}
+// ... and back: the careful decoder's lookahead starts empty at the next unconsumed byte
+LZ_DEV void f2_leave(Dec &d) {
+    d.ip = d.g0 + (d.ips - d.sIn);
+    d.inb_hi = d.inb_lo = 0;
+    d.inbits = 0;
+    d.phantom = 0;
+}
+
 // Decode symbols until the range-coded part ends (Reader1.Read driving
 // decompress(), reader1.go:223-254).  On return d.status / d.site are set and no
 // store is pending.
 template <int kV>
-LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8_t *dict_base) {
+LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8_t *dict_base, uint8_t *inbuf = nullptr) {
     bool fast = false;   // which decoder runs (lzgpu_core.cuh, kFast)
     set_fast_limits(d);
     d.stage = wc.stage;
     for (;;) {
         uint32_t op, len = 0, dist = 0;
+        if (kV & V_CHAIN) {
+            for (;;) {
+                if (fast) {
+                    op = decode_fast2<kV>(d, len, dist);
+                    if (op != OP_SWITCH) break;
+                    // stage used up (refill) or the unit's tail reached (careful decoder from here on)
+                    if (d.outp <= d.fast_out_end && f2_enter<kV>(d, d.g0 + (d.ips - d.sIn), inbuf)) continue;
+                    f2_leave(d);
+                    fast = false;
+                } else {
+                    op = decode_run<kV, false>(d, P, L, len, dist);
+                    if (op != OP_SWITCH) break;
+                    fast = f2_enter<kV>(d, d.ip - (d.inbits >> 3), inbuf);   // true: fast_possible() checked the input left
+                }
+            }
+            if (fast && op == OP_DONE) { f2_leave(d); fast = false; }
+        } else
         for (;;) {
             if (fast) {
                 op = decode_run<kV, true>(d, P, L, len, dist);
@@ -175,7 +240,8 @@ LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8
             LZ_SYNC();
         }
     }
-    if (fast) d.ip -= 4;   // the word loaded ahead was never consumed
+    if (kV & V_CHAIN) { if (fast) f2_leave(d); }
+    else if (fast) d.ip -= 4;   // the word loaded ahead was never consumed
     wc_commit(wc);
 }
 
@@ -193,6 +259,7 @@ struct UnitIO {
     uint8_t *out;            // unit's output
     uint64_t out_cap;
     uint8_t *stage;          // 64 bytes of shared memory, 4-byte aligned (window-copy staging)
+    uint8_t *inbuf;          // kF2Stage bytes of shared memory, 16-byte aligned (V_CHAIN input stage)
 };
 
 // LZMA1 unit (kind RAW; ALONE units are converted by the host).
@@ -208,6 +275,7 @@ LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     wc.stage = io.stage;
     wc.out_limit = io.out + io.out_cap;
     set_props(d, u.lc, u.lp, u.pb);
+    set_shared_addrs(d, P, io.inbuf);
     d.dict_size = u.dict_size;
     d.wpos = 0;
     d.full = 0;
@@ -229,7 +297,7 @@ LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     r = rc_init(d);
     if (r < 0) { d.status = LZGPU_UNEXPECTED_EOF; }                       // "rangeDec.Init: %w" of io.EOF
     else if (r > 0) { d.status = LZGPU_RESULT_ERROR; d.site = LZGPU_SITE_RC_INIT; }
-    else run_lzma<kV>(d, wc, P, L, io.out);
+    else run_lzma<kV>(d, wc, P, L, io.out, io.inbuf);
 
     LZ_IF_LANE0_ONLY {
         res.status = d.status;
@@ -253,6 +321,7 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     wc.stage = io.stage;
     wc.out_limit = io.out + io.out_cap;
     set_props(d, u.lc, u.lp, u.pb);
+    set_shared_addrs(d, P, io.inbuf);
     d.dict_size = u.dict_size;
     d.wpos = 0;
     d.full = 0;
@@ -390,7 +459,7 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
             break;
         }
         reload_context<kV>(d, dict_base);
-        run_lzma<kV>(d, wc, P, L, dict_base);
+        run_lzma<kV>(d, wc, P, L, dict_base, io.inbuf);
 
         // what the chunk did, as seen by every lane
         uint32_t st = (uint32_t)d.status, st_site = (uint32_t)d.site, complete = 0, exact = 0;

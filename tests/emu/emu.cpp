@@ -45,11 +45,14 @@ extern "C" int emu_decode_batch(const lzgpu_unit *units, int64_t n, const uint8_
         uint16_t *P = probs.data(), *L = probs.data() + P_LIT;
         alignas(16) uint8_t stage[64];
         io.stage = stage;
+        alignas(16) uint8_t inbuf[kF2Stage];
+        io.inbuf = inbuf;
         switch (variant) {
             case 0: run_one<0>(u, io, P, L, bits, r); break;
             case 5: run_one<5>(u, io, P, L, bits, r); break;
             case 17: run_one<17>(u, io, P, L, bits, r); break;
             case 21: run_one<21>(u, io, P, L, bits, r); break;
+            case 33: run_one<33>(u, io, P, L, bits, r); break;
             default: run_one<1>(u, io, P, L, bits, r); break;
         }
         if (alone) r.bytes_in += 13;

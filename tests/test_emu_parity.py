@@ -12,7 +12,7 @@ from lzma_b200 import batch as B
 from oracle import oracle as O
 
 
-@pytest.fixture(scope="module", params=[0, 1, 5, 17, 21])
+@pytest.fixture(scope="module", params=[0, 1, 5, 17, 21, 33])
 def ctx(request):
     """Every tuning variant of the decoder (lzgpu_core.cuh V_*) must give identical results."""
     return make_context("emu", request.param)

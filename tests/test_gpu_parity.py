@@ -120,7 +120,7 @@ def test_large_literal_tables_in_hbm(ctx):
         same_outcome(want, g.status, g.err_site, g.data, f"prop{prop}")
 
 
-@pytest.mark.parametrize("variant", [0, 1, 5, 17, 21])
+@pytest.mark.parametrize("variant", [0, 1, 5, 17, 21, 33])
 def test_tuning_variants_agree(variant, monkeypatch):
     """Every decoder tuning variant (LZGPU_VARIANT, lzgpu_core.cuh V_*) is bit-exact."""
     monkeypatch.setenv("LZGPU_VARIANT", str(variant))
