@@ -44,7 +44,7 @@ struct KArgs {
 // One warp per CTA, one unit per warp.  Fixed tables (3.7 KB) always in shared
 // memory; literal tables in shared memory when lc+lp <= 4 (<= 24 KB), else in HBM.
 template <bool kLitGlobal, int kV>
-__global__ void __launch_bounds__(32) lzgpu_decode_kernel(const KArgs a) {
+__global__ void __launch_bounds__(32, 8) lzgpu_decode_kernel(const KArgs a) {
     extern __shared__ __align__(16) uint16_t smem_probs[];
     const uint32_t slot = a.slot0 + blockIdx.x;
     const int32_t ui = a.order[slot];

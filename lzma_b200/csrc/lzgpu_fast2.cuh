@@ -53,12 +53,14 @@ namespace lzgpu {
     "shr.s32 k, k, 5;\n\t"                                                              \
     "add.s32 pn, " P ", k;\n\t"
 // normalisation: consume the byte in hand, fetch the one after it
+// (the address is advanced BEFORE the load: an add placed after it would have to wait until the load has
+// read its address register -- ~10 cycles in every step, measured)
 #define F2_NORM                                                                         \
     "setp.lt.u32 nz, %0, 0x1000000;\n\t"                                                \
+    "@nz add.u32 %3, %3, 1;\n\t"                                                        \
     "@nz shl.b32 %0, %0, 8;\n\t"                                                        \
     "@nz mad.lo.u32 %1, %1, 256, %2;\n\t"                                               \
-    "@nz ld.shared.u8 %2, [%3+1];\n\t"                                                  \
-    "@nz add.u32 %3, %3, 1;\n\t"
+    "@nz ld.shared.u8 %2, [%3];\n\t"
 
 #define F2_LD(Y) "ld.shared.u16 lo, [" Y "];\n\tld.shared.u16 hi, [" Y "+2];\n\t"
 #define F2_NOLD(Y) ""
@@ -125,12 +127,14 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
                  F2_L0("%5", F2_LD) F2_L1(F2_LD) F2_L2(F2_LD) F2_L3(F2_LD) F2_L4(F2_LD) F2_L5(F2_NOLD) \
                  "add.u32 t, yb, nS;\n\tshr.u32 %4, t, 2;\n\t}"                          \
                  : F2_IO(d), "=&r"(OUT) : "r"(BASE) : "memory")
-// 4-level tree (align, decompress.go:580-625, LSB first): result = node index 16..31, bits MSB-first
-#define F2_TREE4(d, OUT, BASE)                                                          \
-    asm volatile("{\n\t" F2_REGS F2_ROOT("%5")                                          \
+// 4-level tree (align, decompress.go:580-625, LSB first): result = node index 16..31, bits MSB-first.
+// The root and its children (P0, PLO, PHI) were loaded by the caller before the direct bits.
+#define F2_TREE4(d, OUT, BASE, P0, PLO, PHI)                                            \
+    asm volatile("{\n\t" F2_REGS                                                        \
+                 "neg.s32 nS, %5;\n\tmov.b32 p, %6;\n\tmov.b32 lo, %7;\n\tmov.b32 hi, %8;\n\tadd.u32 yb, %5, 4;\n\t" \
                  F2_L0("%5", F2_LD) F2_L1(F2_LD) F2_L2(F2_LD) F2_L3(F2_NOLD)            \
                  "add.u32 t, yc, nS;\n\tshr.u32 %4, t, 2;\n\t}"                          \
-                 : F2_IO(d), "=&r"(OUT) : "r"(BASE) : "memory")
+                 : F2_IO(d), "=&r"(OUT) : "r"(BASE), "r"(P0), "r"(PLO), "r"(PHI) : "memory")
 
 // lenDecoder.Decode (len_decoder.go:34-60; live copies decompress.go:218-429, 870-1118).
 // SLEN = byte address of the coder, SLOW = byte address of its low tree for this posState
@@ -258,29 +262,48 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
 
 // consume one input byte outside an adaptive step (direct bits, decompress.go:549-576)
 #define F2_SHIFT8(d)                                                                    \
-    asm volatile("shl.b32 %0, %0, 8;\n\t"                                               \
+    asm volatile("add.u32 %3, %3, 1;\n\t"                                               \
+                 "shl.b32 %0, %0, 8;\n\t"                                               \
                  "mad.lo.u32 %1, %1, 256, %2;\n\t"                                      \
-                 "ld.shared.u8 %2, [%3+1];\n\t"                                         \
-                 "add.u32 %3, %3, 1;"                                                   \
+                 "ld.shared.u8 %2, [%3];"                                               \
                  : F2_IO(d) : : "memory")
 
 #define F2_FAIL(ST, SITE) do { d.status = (ST); d.site = (SITE); return OP_DONE; } while (0)
 
-// Same contract as decode_run<kV, true>: runs until a symbol needs the warp (OP_COPY / OP_COPY_Q4 with
-// len and dist set), the unit part ends (OP_DONE) or the staged input / the output margin is used up
-// (OP_SWITCH: the caller refills the stage or hands over to the careful decoder).
+// predicated byte store / load of the window copy: no branch, no convergence barrier
+#define F2_ST8_IF(PTR, VAL, LANE, N)                                                    \
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %2, %3;\n\t@q st.global.u8 [%0], %1;\n\t}" \
+                 : : "l"(PTR), "r"(VAL), "r"(LANE), "r"(N) : "memory")
+#define F2_LD8_IF(VAL, PTR, LANE, N)                                                    \
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %2, %3;\n\t@q ld.global.u8 %0, [%1];\n\t}" \
+                 : "+r"(VAL) : "l"(PTR), "r"(LANE), "r"(N) : "memory")
+
+// Same contract as decode_run<kV, true>, except that the common window copy (<= 32 bytes, not
+// overlapping itself) is done right here: returns when a symbol needs the general copy code (OP_COPY /
+// OP_COPY_Q4 with len and dist set), the unit part ends (OP_DONE) or the staged input / the output
+// margin is used up (OP_SWITCH: the caller refills the stage or hands over to the careful decoder).
 template <int kV>
-__device__ __forceinline__ uint32_t decode_fast2(Dec &d, uint32_t &out_len, uint32_t &out_dist) {
+__device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t &out_len, uint32_t &out_dist) {
     const uint32_t sP = d.sP;
+    const uint32_t lane = LZ_LANE();
+    // the next symbol's isMatch / isRep probabilities are loaded as soon as the current symbol has fixed
+    // the state and the position they depend on (nothing in between touches those cells)
+    uint32_t pos_state = d.wpos & d.pos_mask;                    // decompress.go:22
+    uint32_t a_im = sP + 2u * P_IS_MATCH + 2u * ((d.state << 4) + pos_state);   // :23
+    uint32_t a_rep = sP + 2u * P_REP4 + 8u * d.state;
+    uint32_t p_im = f2_lds16(a_im);
+    uint32_t p_rep = f2_lds16(a_rep);
+#define F2_NEXT_CTX()                                                                   \
+    do {                                                                                \
+        pos_state = d.wpos & d.pos_mask;                                                \
+        a_im = sP + 2u * P_IS_MATCH + 2u * ((d.state << 4) + pos_state);                \
+        a_rep = sP + 2u * P_REP4 + 8u * d.state;                                        \
+        p_im = f2_lds16(a_im);                                                          \
+        p_rep = f2_lds16(a_rep);                                                        \
+    } while (0)
     for (;;) {
         if (LZ_UNLIKELY(d.ips > d.lims || d.outp > d.fast_out_end)) return OP_SWITCH;
 
-        const uint32_t pos_state = d.wpos & d.pos_mask;          // decompress.go:22
-        const uint32_t state2 = (d.state << 4) + pos_state;      // :23
-        const uint32_t a_im = sP + 2u * P_IS_MATCH + 2u * state2;
-        const uint32_t a_rep = sP + 2u * P_REP4 + 8u * d.state;
-        const uint32_t p_im = f2_lds16(a_im);
-        const uint32_t p_rep = f2_lds16(a_rep);                  // in flight while isMatch decodes
         uint32_t bit;
         F2_BIT(d, p_im, a_im, bit);                              // :25-42
 
@@ -292,23 +315,34 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, uint32_t &out_len, uint
             }
             d.ctx_pending = 0;
             const uint32_t S = d.sL + 0x600u * (((d.wpos & d.lp_mask) << d.lc) + (prevb >> (8 - d.lc)));  // :56-57
-            uint32_t sym;
-            F2_LIT(d, sym, S, 0x100u | matchb, d.state >= 7 ? 1u : 0u);
-            *d.outp++ = (uint8_t)sym;                             // PutByte, :168
-            d.prev_byte = sym;
+            const uint32_t matched = d.state >= 7 ? 1u : 0u;
+            d.state = d.state < 4 ? 0 : (d.state < 10 ? d.state - 3 : d.state - 6);  // stateUpdateLiteral
             d.wpos++;
             if (LZ_UNLIKELY(d.wpos >= d.dict_size)) { d.wpos -= d.dict_size; d.full = 1; }
-            d.state = d.state < 4 ? 0 : (d.state < 10 ? d.state - 3 : d.state - 6);  // stateUpdateLiteral
+            F2_NEXT_CTX();
+            uint32_t sym;
+            F2_LIT(d, sym, S, 0x100u | matchb, matched);
+            *d.outp++ = (uint8_t)sym;                             // PutByte, :168
+            d.prev_byte = sym;
             continue;
         }
 
         uint32_t len;
+        const uint32_t state2 = (a_im - sP - 2u * P_IS_MATCH) >> 1;   // of THIS symbol (isRep0Long, :716)
+        const uint32_t a_rep_cur = a_rep, pos_state_cur = pos_state;
         F2_BIT(d, p_rep, a_rep, bit);                             // isRep, :195-213
-        if (bit == 0) {  // simple match, :215-668
+        if (LZ_LIKELY(bit == 0)) {  // simple match, :215-668
             d.rep3 = d.rep2; d.rep2 = d.rep1; d.rep1 = d.rep0;    // :216
-            F2_LEN(d, len, sP + 2u * P_LEN0, sP + 2u * (P_LEN0 + LEN_LOW) + 16u * pos_state);   // :218-429
+            F2_LEN(d, len, sP + 2u * P_LEN0, sP + 2u * (P_LEN0 + LEN_LOW) + 16u * pos_state_cur);   // :218-429
             d.state = d.state < 7 ? 7 : 10;                       // stateUpdateMatch, :431
             const uint32_t len_state = len > 3 ? 3 : len;         // :434-437
+            len += 2;                                             // :656
+            // window position after this match: fixes the next symbol's contexts (the checks below read
+            // the position before it, kept in wpos0)
+            const uint32_t wpos0 = d.wpos;
+            d.wpos += len;
+            if (LZ_UNLIKELY(d.wpos >= d.dict_size)) { d.wpos -= d.dict_size; d.full |= 2; }   // bit 1: became full by THIS match
+            F2_NEXT_CTX();
             uint32_t slot;
             F2_TREE6(d, slot, sP + 2u * P_POS_SLOT + (len_state << 7));   // :441-486
             slot -= 64;
@@ -331,6 +365,9 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, uint32_t &out_len, uint
                     }
                     dist += v;
                 } else {                                          // :548-628
+                    // the align tree's root and its children: in flight during the direct bits
+                    const uint32_t al0 = f2_lds16(sP + 2u * P_ALIGN + 2), al2 = f2_lds16(sP + 2u * P_ALIGN + 4),
+                                   al3 = f2_lds16(sP + 2u * P_ALIGN + 6);
                     // DecodeDirectBits: as in decode_run (runs of halvings between normalisations)
                     uint32_t res = 0;
                     uint32_t n = nd - 4;                           // 1..26
@@ -360,25 +397,35 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, uint32_t &out_len, uint
                     }
                     dist += res << 4;
                     uint32_t m;
-                    F2_TREE4(d, m, sP + 2u * P_ALIGN);            // :580-625
+                    F2_TREE4(d, m, sP + 2u * P_ALIGN, al0, al2, al3);   // :580-625
                     dist += __brev(m) >> 28;
                 }
                 d.rep0 = dist;
             }
-            if (LZ_UNLIKELY(d.rep0 == 0xFFFFFFFFu)) {             // EOS marker, :633-645 (never at the declared end here)
-                if (d.code == 0) {
-                    if (d.size_defined) F2_FAIL(LZGPU_RESULT_ERROR, 636);
-                    F2_FAIL(LZGPU_OK, 0);
+            // One test for everything unusual about the distance: ordinary ones are below the number of
+            // bytes the window held BEFORE this match.  The EOS marker (0xFFFFFFFF) is never ordinary.
+            const uint32_t full0 = d.full & 1u;
+            if (LZ_UNLIKELY(d.rep0 >= (full0 ? d.dict_size : wpos0))) {
+                if (d.rep0 == 0xFFFFFFFFu) {                      // EOS marker, :633-645 (never at the declared end here)
+                    if (d.code == 0) {
+                        if (d.size_defined) F2_FAIL(LZGPU_RESULT_ERROR, 636);
+                        F2_FAIL(LZGPU_OK, 0);
+                    }
+                    F2_FAIL(LZGPU_RESULT_ERROR, 643);
                 }
-                F2_FAIL(LZGPU_RESULT_ERROR, 643);
+                if (d.rep0 >= d.dict_size || !(full0 || d.rep0 <= wpos0))   // :651-653 (Q4 as written)
+                    F2_FAIL(LZGPU_RESULT_ERROR, 652);
+                // rep0 == wpos0 on a window that is not full: the reference's off-by-one (Q4)
+                d.full = (d.full | (d.full >> 1)) & 1u;
+                out_len = len;
+                out_dist = d.rep0 + 1;
+                return OP_COPY_Q4;
             }
-            if (LZ_UNLIKELY(d.rep0 >= d.dict_size || !(d.full || d.rep0 <= d.wpos)))  // :651-653 (Q4 as written)
-                F2_FAIL(LZGPU_RESULT_ERROR, 652);
-            len += 2;                                             // :656
-        } else {  // rep match, :685-1118
+            d.full = (d.full | (d.full >> 1)) & 1u;
+        } else {  // rep match, :685-1118 (rare here: the generic single-bit steps)
             if (LZ_UNLIKELY(d.wpos == 0 && !d.full)) F2_FAIL(LZGPU_RESULT_ERROR, 691);  // IsEmpty, :690-692
             bool short_rep = false;
-            uint32_t a = a_rep + 2, pv = f2_lds16(a);
+            uint32_t a = a_rep_cur + 2, pv = f2_lds16(a);
             F2_BIT(d, pv, a, bit);                                // isRepG0, :694-772
             if (bit == 0) {
                 a = sP + 2u * P_IS_REP0_LONG + 2u * state2;
@@ -387,13 +434,13 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, uint32_t &out_len, uint
                 short_rep = (bit == 0);
             } else {
                 uint32_t dist;
-                a = a_rep + 4;
+                a = a_rep_cur + 4;
                 pv = f2_lds16(a);
                 F2_BIT(d, pv, a, bit);                            // isRepG1, :777-813
                 if (bit == 0) {
                     dist = d.rep1; d.rep1 = d.rep0; d.rep0 = dist;
                 } else {
-                    a = a_rep + 6;
+                    a = a_rep_cur + 6;
                     pv = f2_lds16(a);
                     F2_BIT(d, pv, a, bit);                        // isRepG2, :816-861
                     if (bit == 0) { dist = d.rep2; d.rep2 = d.rep1; d.rep1 = d.rep0; d.rep0 = dist; }
@@ -404,30 +451,52 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, uint32_t &out_len, uint
                 d.state = d.state < 7 ? 9 : 11;                   // stateUpdateShortRep
                 len = 1;
             } else {
-                F2_LEN(d, len, sP + 2u * P_LEN1, sP + 2u * (P_LEN1 + LEN_LOW) + 16u * pos_state);   // :870-1101
+                F2_LEN(d, len, sP + 2u * P_LEN1, sP + 2u * (P_LEN1 + LEN_LOW) + 16u * pos_state_cur);   // :870-1101
                 d.state = d.state < 7 ? 8 : 11;                   // stateUpdateRep
                 len += 2;
             }
+            const uint32_t dist = d.rep0 + 1;
+            if (LZ_UNLIKELY(!d.full && dist > d.wpos)) {
+                if (dist != d.wpos + 1) F2_FAIL(LZGPU_RESULT_ERROR, LZGPU_SITE_REP_BEFORE_DICT);   // Q5
+                d.wpos += len;
+                if (LZ_UNLIKELY(d.wpos >= d.dict_size)) { d.wpos -= d.dict_size; d.full = 1; }
+                out_len = len;
+                out_dist = dist;
+                return OP_COPY_Q4;                                // Q4
+            }
+            d.wpos += len;
+            if (LZ_UNLIKELY(d.wpos >= d.dict_size)) { d.wpos -= d.dict_size; d.full = 1; }
+            F2_NEXT_CTX();
         }
 
         // copy: decompress.go:656-668 / :934-947 / :1028-1041 / :1104-1117 (sizes cannot be exceeded here)
         const uint32_t dist = d.rep0 + 1;
-        uint32_t op = OP_COPY;
-        if (LZ_UNLIKELY(!d.full && dist > d.wpos)) {
-            if (dist != d.wpos + 1) F2_FAIL(LZGPU_RESULT_ERROR, LZGPU_SITE_REP_BEFORE_DICT);   // Q5
-            op = OP_COPY_Q4;                                      // Q4
+        if (LZ_UNLIKELY(len > 32 || dist <= len)) {   // long or self-overlapping: the general copy code
+            out_len = len;
+            out_dist = dist;
+            return OP_COPY;
         }
-        d.wpos += len;
-        if (LZ_UNLIKELY(d.wpos >= d.dict_size)) { d.wpos -= d.dict_size; d.full = 1; }
-        out_len = len;
-        out_dist = dist;
-        return op;
+        // window.CopyMatch (window.go:55-87) for the common case: lane j moves byte j.  The previous
+        // match's bytes are stored first (they were held back so that nothing waited for their loads).
+        uint8_t *dst = d.outp;
+        F2_ST8_IF(wc.pend_dst + lane, wc.pend_val, lane, wc.pend_len);
+        __syncwarp();
+        const uint8_t *src = dst - dist;
+        F2_LD8_IF(wc.pend_val, src + lane, lane, len);
+        LZ_LD_WIN8(d.ctx_a, src + (len - 1));                     // context of a literal that may follow:
+        LZ_LD_WIN8(d.ctx_b, src + len);                           // last byte of the match, byte at -(rep0+1) after it
+        d.ctx_pending = 1;
+        wc.pend_len = len;
+        wc.pend_dst = dst;
+        wc.pend_staged = 0;
+        d.outp = dst + len;
     }
+#undef F2_NEXT_CTX
 }
 
 #else   // host passes: never called (fast_possible<V_CHAIN> is false off the device)
 template <int kV>
-LZ_HD uint32_t decode_fast2(Dec &, uint32_t &, uint32_t &) { return OP_DONE; }
+LZ_HD uint32_t decode_fast2(Dec &, WarpCopy &, uint32_t &, uint32_t &) { return OP_DONE; }
 #endif
 
 }  // namespace lzgpu

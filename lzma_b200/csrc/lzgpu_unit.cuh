@@ -15,7 +15,6 @@
 // uncompressedRead (reader2.go:100-294) for LZMA2 groups.
 #pragma once
 #include "lzgpu_core.cuh"
-#include "lzgpu_fast2.cuh"
 
 #if defined(__CUDA_ARCH__)
 #define LZ_LANE() (threadIdx.x & 31u)
@@ -45,8 +44,14 @@ struct WarpCopy {
     uint32_t pend_dist;    // staged: match distance (period of an overlapping copy)
     uint8_t *stage;        // 64-byte shared staging buffer of the warp (V_STAGE)
     uint8_t *out_limit;    // end of the unit's output range (staging over-reads <= 3 bytes)
-    LZ_LANEVAR(uint8_t, pend_val);
+    LZ_LANEVAR(uint32_t, pend_val);   // the byte, in a 32-bit register
 };
+
+}  // namespace lzgpu
+
+#include "lzgpu_fast2.cuh"   // needs WarpCopy and the lane macros
+
+namespace lzgpu {
 
 // Store the previous match's bytes.  They reach memory before anything can read them: this runs
 // ahead of every window fetch.
@@ -60,7 +65,7 @@ LZ_DEV void wc_commit(WarpCopy &wc) {
             }
         } else {
             LZ_FOR_LANES(l) {
-                if (l < wc.pend_len) wc.pend_dst[l] = LZ_LV(wc.pend_val, l);
+                if (l < wc.pend_len) wc.pend_dst[l] = (uint8_t)LZ_LV(wc.pend_val, l);
             }
         }
         wc.pend_len = 0;
@@ -149,7 +154,7 @@ LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8
         if (kV & V_CHAIN) {
             for (;;) {
                 if (fast) {
-                    op = decode_fast2<kV>(d, len, dist);
+                    op = decode_fast2<kV>(d, wc, len, dist);
                     if (op != OP_SWITCH) break;
                     // stage used up (refill) or the unit's tail reached (careful decoder from here on)
                     if (d.outp <= d.fast_out_end && f2_enter<kV>(d, d.g0 + (d.ips - d.sIn), inbuf)) continue;

@@ -1,0 +1,8 @@
+#!/bin/bash
+# ncu full captures of the decode kernel in the lone-warp shape (148 units) and the bench shape (1024 units)
+mkdir -p gpurun_out
+V=${LZGPU_VARIANT:-33}
+export LZGPU_VARIANT=$V
+timeout 300 python scripts/bench_corpora.py --quick 2>&1 | tail -2
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:lzgpu_decode -s 2 -c 1 -o gpurun_out/prof148_v$V -f python scripts/bench_corpora.py --quick > gpurun_out/ncu148.log 2>&1; tail -1 gpurun_out/ncu148.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:lzgpu_decode -s 7 -c 1 -o gpurun_out/prof1024_v$V -f python scripts/bench_corpora.py --quick > gpurun_out/ncu1024.log 2>&1; tail -1 gpurun_out/ncu1024.log
