@@ -36,9 +36,12 @@ namespace lzgpu {
 //   %4 the block's result, %5.. its inputs.
 #define F2_REGS                                                                         \
     ".reg .pred one, nz, q0, q1, mbp, ne;\n\t"                                          \
-    ".reg .b32 t, bd, k, pn, p, lo, hi, ya, yb, yc, nS;\n\t"
+    ".reg .b32 t, bd, k, pn, p, pz, lo, hi, ya, yb, yc, nS;\n\t"
 
-// DecodeBit arithmetic (range_decoder.go:57-98) on probability register P; predicate Q = the bit.
+// DecodeBit (range_decoder.go:57-98) on probability register P, predicate Q = the bit, followed by the
+// normalisation: consume the byte in hand, fetch the one after it.  Ordered along the critical path.
+// (The input address is advanced BEFORE the load: an add placed after it would have to wait until the
+// load has read its address register -- ~10 cycles in every step, measured.)
 #define F2_CORE(P, Q)                                                                   \
     "shr.u32 t, %0, 11;\n\t"                                                            \
     "mul.lo.u32 bd, t, " P ";\n\t"                                                      \
@@ -46,56 +49,64 @@ namespace lzgpu {
     "setp.ge.u32 " Q ", %1, bd;\n\t"                                                    \
     "sub.u32 t, %0, bd;\n\t"                                                            \
     "selp.b32 %0, t, bd, " Q ";\n\t"                                                    \
-    "@" Q " sub.u32 %1, %1, bd;\n\t"
+    "setp.lt.u32 nz, %0, 0x1000000;\n\t"                                                \
+    "@" Q " sub.u32 %1, %1, bd;\n\t"                                                    \
+    "@nz shl.b32 %0, %0, 8;\n\t"                                                        \
+    "@nz add.u32 %3, %3, 1;\n\t"                                                        \
+    "@nz mad.lo.u32 %1, %1, 256, %2;\n\t"                                               \
+    "@nz ld.shared.u8 %2, [%3];\n\t"
 // pn = P + ((Q ? 31 : 2048) - P) >> 5   (p - (p >> 5) for a 1, p + ((2048 - p) >> 5) for a 0)
 #define F2_UPD(P, Q)                                                                    \
     "@!" Q " sub.s32 k, 2048, " P ";\n\t"                                               \
     "shr.s32 k, k, 5;\n\t"                                                              \
     "add.s32 pn, " P ", k;\n\t"
-// normalisation: consume the byte in hand, fetch the one after it
-// (the address is advanced BEFORE the load: an add placed after it would have to wait until the load has
-// read its address register -- ~10 cycles in every step, measured)
-#define F2_NORM                                                                         \
-    "setp.lt.u32 nz, %0, 0x1000000;\n\t"                                                \
-    "@nz add.u32 %3, %3, 1;\n\t"                                                        \
-    "@nz shl.b32 %0, %0, 8;\n\t"                                                        \
-    "@nz mad.lo.u32 %1, %1, 256, %2;\n\t"                                               \
-    "@nz ld.shared.u8 %2, [%3];\n\t"
+#define F2_NORM ""   /* part of F2_CORE */
 
 #define F2_LD(Y) "ld.shared.u16 lo, [" Y "];\n\tld.shared.u16 hi, [" Y "+2];\n\t"
 #define F2_NOLD(Y) ""
-// One level of a heap-ordered bit tree.  On entry: p = probability of the current node, lo / hi =
+// One level of a heap-ordered bit tree.  On entry: P = probability of the current node, lo / hi =
 // its children's, loaded from [YC] / [YC+2] (YC = base + 4m).  The node itself lives at YP + (QP ? 2 : 0).
-// On exit YN = pair address of the chosen child's children (loaded if LOADS), p = the chosen child's.
-#define F2_STEP(YP, QP, YC, YN, QC, NS, LOADS)                                          \
-    F2_CORE("p", QC)                                                                    \
+// On exit YN = pair address of the chosen child's children (loaded if LOADS), PN = the chosen child's.
+// Instruction ORDER follows the critical path (range -> bound -> bit -> range -> normalised range): ptxas
+// breaks scheduling ties by source order.
+#define F2_STEP_BODY(YC, YN, QC, NS, LOADS, P, PN, STORE)                               \
+    "shr.u32 t, %0, 11;\n\t"                                                            \
+    "mul.lo.u32 bd, t, " P ";\n\t"                                                      \
     "mad.lo.u32 " YN ", " YC ", 2, " NS ";\n\t"                                         \
+    "sub.s32 k, 31, " P ";\n\t"                                                         \
+    "setp.ge.u32 " QC ", %1, bd;\n\t"                                                   \
+    "sub.u32 t, %0, bd;\n\t"                                                            \
+    "selp.b32 %0, t, bd, " QC ";\n\t"                                                   \
+    "selp.b32 " PN ", hi, lo, " QC ";\n\t"                                              \
+    "setp.lt.u32 nz, %0, 0x1000000;\n\t"                                                \
+    "@" QC " sub.u32 %1, %1, bd;\n\t"                                                   \
     "@" QC " add.u32 " YN ", " YN ", 4;\n\t"                                            \
-    F2_UPD("p", QC)                                                                     \
-    "selp.b32 p, hi, lo, " QC ";\n\t"                                                   \
+    "@nz shl.b32 %0, %0, 8;\n\t"                                                        \
+    "@nz add.u32 %3, %3, 1;\n\t"                                                        \
+    "@nz mad.lo.u32 %1, %1, 256, %2;\n\t"                                               \
     LOADS(YN)                                                                           \
-    "@" QP " st.shared.u16 [" YP "+2], pn;\n\t"                                         \
-    "@!" QP " st.shared.u16 [" YP "], pn;\n\t"                                          \
-    F2_NORM
+    "@nz ld.shared.u8 %2, [%3];\n\t"                                                    \
+    "@!" QC " sub.s32 k, 2048, " P ";\n\t"                                              \
+    "shr.s32 k, k, 5;\n\t"                                                              \
+    "add.s32 pn, " P ", k;\n\t"                                                         \
+    STORE
+#define F2_STEP(YP, QP, YC, YN, QC, NS, LOADS, P, PN)                                   \
+    F2_STEP_BODY(YC, YN, QC, NS, LOADS, P, PN,                                          \
+                 "@" QP " st.shared.u16 [" YP "+2], pn;\n\t"                            \
+                 "@!" QP " st.shared.u16 [" YP "], pn;\n\t")
 // the root level: node at [BASE+2]
-#define F2_STEP0(BASE, YC, YN, QC, NS, LOADS)                                           \
-    F2_CORE("p", QC)                                                                    \
-    "mad.lo.u32 " YN ", " YC ", 2, " NS ";\n\t"                                         \
-    "@" QC " add.u32 " YN ", " YN ", 4;\n\t"                                            \
-    F2_UPD("p", QC)                                                                     \
-    "selp.b32 p, hi, lo, " QC ";\n\t"                                                   \
-    LOADS(YN)                                                                           \
-    "st.shared.u16 [" BASE "+2], pn;\n\t"                                               \
-    F2_NORM
-// levels by depth; the pair-address registers rotate yb -> yc -> ya, the predicates alternate
-#define F2_L0(BASE, LOADS) F2_STEP0(BASE, "yb", "yc", "q0", "nS", LOADS)
-#define F2_L1(LOADS) F2_STEP("yb", "q0", "yc", "ya", "q1", "nS", LOADS)
-#define F2_L2(LOADS) F2_STEP("yc", "q1", "ya", "yb", "q0", "nS", LOADS)
-#define F2_L3(LOADS) F2_STEP("ya", "q0", "yb", "yc", "q1", "nS", LOADS)
-#define F2_L4(LOADS) F2_STEP("yb", "q1", "yc", "ya", "q0", "nS", LOADS)
-#define F2_L5(LOADS) F2_STEP("yc", "q0", "ya", "yb", "q1", "nS", LOADS)
-#define F2_L6(LOADS) F2_STEP("ya", "q1", "yb", "yc", "q0", "nS", LOADS)
-#define F2_L7(LOADS) F2_STEP("yb", "q0", "yc", "ya", "q1", "nS", LOADS)
+#define F2_STEP0(BASE, YC, YN, QC, NS, LOADS, P, PN)                                    \
+    F2_STEP_BODY(YC, YN, QC, NS, LOADS, P, PN, "st.shared.u16 [" BASE "+2], pn;\n\t")
+// levels by depth; the pair-address registers rotate yb -> yc -> ya, the predicates and the
+// probability registers (p, pz) alternate
+#define F2_L0(BASE, LOADS) F2_STEP0(BASE, "yb", "yc", "q0", "nS", LOADS, "p", "pz")
+#define F2_L1(LOADS) F2_STEP("yb", "q0", "yc", "ya", "q1", "nS", LOADS, "pz", "p")
+#define F2_L2(LOADS) F2_STEP("yc", "q1", "ya", "yb", "q0", "nS", LOADS, "p", "pz")
+#define F2_L3(LOADS) F2_STEP("ya", "q0", "yb", "yc", "q1", "nS", LOADS, "pz", "p")
+#define F2_L4(LOADS) F2_STEP("yb", "q1", "yc", "ya", "q0", "nS", LOADS, "p", "pz")
+#define F2_L5(LOADS) F2_STEP("yc", "q0", "ya", "yb", "q1", "nS", LOADS, "pz", "p")
+#define F2_L6(LOADS) F2_STEP("ya", "q1", "yb", "yc", "q0", "nS", LOADS, "p", "pz")
+#define F2_L7(LOADS) F2_STEP("yb", "q0", "yc", "ya", "q1", "nS", LOADS, "pz", "p")
 // pair address after n levels: n=3 -> yb, 4 -> yc, 6 -> yb, 8 -> ya; node index m = (y - base) >> 2
 #define F2_ROOT(BASE)                                                                   \
     "neg.s32 nS, " BASE ";\n\t"                                                         \
@@ -137,51 +148,64 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
                  : F2_IO(d), "=&r"(OUT) : "r"(BASE), "r"(P0), "r"(PLO), "r"(PHI) : "memory")
 
 // lenDecoder.Decode (len_decoder.go:34-60; live copies decompress.go:218-429, 870-1118).
-// SLEN = byte address of the coder, SLOW = byte address of its low tree for this posState
-// (mid tree = SLOW + 256, high tree = SLEN + 528).  Result 0..271.
+// SLEN (%5) = byte address of the coder, SLOW (%6) = byte address of its low tree for this posState
+// (mid tree = SLOW + 256, high tree = SLEN + 528).  Result 0..271.  The choice cells and the low
+// tree's root and children are loaded by F2_LEN_LOADS, which the caller places as early as it can.
+#define F2_LEN_LOADS                                                                    \
+    "ld.shared.u16 p, [%5];\n\t"                                                        \
+    "ld.shared.u16 pc2, [%5+2];\n\t"                                                    \
+    "ld.shared.u16 pr0, [%6+2];\n\t"                                                    \
+    "ld.shared.u16 lo, [%6+4];\n\t"                                                     \
+    "ld.shared.u16 hi, [%6+6];\n\t"
+#define F2_LEN_BODY(L)                                                                  \
+    F2_CORE("p", "one") F2_UPD("p", "one")                                              \
+    "st.shared.u16 [%5], pn;\n\t"                                                       \
+    "@one bra.uni " L "CH2;\n\t"                                                        \
+    "mov.b32 bs, %6;\n\t"                                                               \
+    "mov.b32 p, pr0;\n\t"                                                               \
+    "mov.u32 %4, 0xfffffff8;\n\t"                                                       \
+    "bra.uni " L "T3;\n\t"                                                              \
+    L "CH2:\n\t"                                                                        \
+    "add.u32 bs, %6, 256;\n\t"                                                          \
+    "ld.shared.u16 pr0, [bs+2];\n\t"                                                    \
+    "ld.shared.u16 lo, [bs+4];\n\t"                                                     \
+    "ld.shared.u16 hi, [bs+6];\n\t"                                                     \
+    F2_CORE("pc2", "one") F2_UPD("pc2", "one")                                          \
+    "st.shared.u16 [%5+2], pn;\n\t"                                                     \
+    "@one bra.uni " L "HI;\n\t"                                                         \
+    "mov.b32 p, pr0;\n\t"                                                               \
+    "mov.u32 %4, 0;\n\t"                                                                \
+    L "T3:\n\t"                                                                         \
+    "neg.s32 nS, bs;\n\t"                                                               \
+    "add.u32 yb, bs, 4;\n\t"                                                            \
+    F2_L0("bs", F2_LD) F2_L1(F2_LD) F2_L2(F2_NOLD)                                      \
+    "add.u32 t, yb, nS;\n\t"                                                            \
+    "shr.u32 t, t, 2;\n\t"                                                              \
+    "add.u32 %4, %4, t;\n\t"                                                            \
+    "bra.uni " L "END;\n\t"                                                             \
+    L "HI:\n\t"                                                                         \
+    "add.u32 bs, %5, 528;\n\t"                                                          \
+    F2_ROOT("bs")                                                                       \
+    F2_L0("bs", F2_LD) F2_L1(F2_LD) F2_L2(F2_LD) F2_L3(F2_LD) F2_L4(F2_LD) F2_L5(F2_LD) F2_L6(F2_LD) F2_L7(F2_NOLD) \
+    "add.u32 t, ya, nS;\n\t"                                                            \
+    "shr.u32 t, t, 2;\n\t"                                                              \
+    "add.u32 %4, t, 0xffffff10;\n\t"                                                    \
+    L "END:\n\t"
 #define F2_LEN(d, OUT, SLEN, SLOW)                                                      \
     asm volatile("{\n\t" F2_REGS ".reg .b32 bs, pc2, pr0;\n\t"                          \
-                 "ld.shared.u16 p, [%5];\n\t"                                           \
-                 "ld.shared.u16 pc2, [%5+2];\n\t"                                       \
-                 "ld.shared.u16 pr0, [%6+2];\n\t"                                       \
-                 "ld.shared.u16 lo, [%6+4];\n\t"                                        \
-                 "ld.shared.u16 hi, [%6+6];\n\t"                                        \
-                 F2_CORE("p", "one") F2_UPD("p", "one")                                 \
-                 "st.shared.u16 [%5], pn;\n\t"                                          \
-                 F2_NORM                                                                \
-                 "@one bra.uni F2_LEN_CH2;\n\t"                                         \
-                 "mov.b32 bs, %6;\n\t"                                                  \
-                 "mov.b32 p, pr0;\n\t"                                                  \
-                 "mov.u32 %4, 0xfffffff8;\n\t"                                          \
-                 "bra.uni F2_LEN_T3;\n\t"                                               \
-                 "F2_LEN_CH2:\n\t"                                                      \
-                 "add.u32 bs, %6, 256;\n\t"                                             \
-                 "ld.shared.u16 pr0, [bs+2];\n\t"                                       \
-                 "ld.shared.u16 lo, [bs+4];\n\t"                                        \
-                 "ld.shared.u16 hi, [bs+6];\n\t"                                        \
-                 F2_CORE("pc2", "one") F2_UPD("pc2", "one")                             \
-                 "st.shared.u16 [%5+2], pn;\n\t"                                        \
-                 F2_NORM                                                                \
-                 "@one bra.uni F2_LEN_HI;\n\t"                                          \
-                 "mov.b32 p, pr0;\n\t"                                                  \
-                 "mov.u32 %4, 0;\n\t"                                                   \
-                 "F2_LEN_T3:\n\t"                                                       \
-                 "neg.s32 nS, bs;\n\t"                                                  \
-                 "add.u32 yb, bs, 4;\n\t"                                               \
-                 F2_L0("bs", F2_LD) F2_L1(F2_LD) F2_L2(F2_NOLD)                         \
-                 "add.u32 t, yb, nS;\n\t"                                               \
-                 "shr.u32 t, t, 2;\n\t"                                                 \
-                 "add.u32 %4, %4, t;\n\t"                                               \
-                 "bra.uni F2_LEN_END;\n\t"                                              \
-                 "F2_LEN_HI:\n\t"                                                       \
-                 "add.u32 bs, %5, 528;\n\t"                                             \
-                 F2_ROOT("bs")                                                          \
-                 F2_L0("bs", F2_LD) F2_L1(F2_LD) F2_L2(F2_LD) F2_L3(F2_LD) F2_L4(F2_LD) F2_L5(F2_LD) F2_L6(F2_LD) F2_L7(F2_NOLD) \
-                 "add.u32 t, ya, nS;\n\t"                                               \
-                 "shr.u32 t, t, 2;\n\t"                                                 \
-                 "add.u32 %4, t, 0xffffff10;\n\t"                                       \
-                 "F2_LEN_END:\n\t}"                                                     \
+                 F2_LEN_LOADS F2_LEN_BODY("F2_LEN_") "}"                                \
                  : F2_IO(d), "=&r"(OUT) : "r"(SLEN), "r"(SLOW) : "memory")
+// isRep (decompress.go:195-213; cell at AREP, value PREP loaded earlier) and, when it decodes 0, the
+// match length: the length coder's cells are in flight while isRep decodes.  OUT = 0xFFFFFFFF for a rep.
+#define F2_ISREP_LEN(d, OUT, SLEN, SLOW, AREP, PREP)                                    \
+    asm volatile("{\n\t" F2_REGS ".reg .b32 bs, pc2, pr0;\n\t"                          \
+                 F2_LEN_LOADS                                                           \
+                 F2_CORE("%8", "one") F2_UPD("%8", "one")                               \
+                 "st.shared.u16 [%7], pn;\n\t"                                          \
+                 "mov.u32 %4, 0xffffffff;\n\t"                                          \
+                 "@one bra.uni F2_RL_END;\n\t"                                          \
+                 F2_LEN_BODY("F2_RL_") "}"                                              \
+                 : F2_IO(d), "=&r"(OUT) : "r"(SLEN), "r"(SLOW), "r"(AREP), "r"(PREP) : "memory")
 
 // ---- literal (decompress.go:49-169).  %5 = byte address S of the context's 0x300 cells,
 // %6 = 0x100 | match byte, %7 != 0: matched mode (state >= 7).  Result = the byte.
@@ -201,9 +225,9 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
     F2_NORM                                                                             \
     "@ne bra.uni " MIS ";\n\t"
 // mismatch at level i: enter plain level i+1 at node v (YP / QP / YC are that level's names)
-#define F2_MIS(LABEL, YP, QP, YC, TARGET)                                               \
+#define F2_MIS(LABEL, YP, QP, YC, TARGET, P)                                            \
     LABEL ":\n\t"                                                                       \
-    "mov.b32 p, pmis;\n\t"                                                              \
+    "mov.b32 " P ", pmis;\n\t"                                                            \
     "mov.b32 " YP ", v;\n\t"                                                            \
     "setp.lt.u32 " QP ", %5, 0;\n\t"                                                    \
     "mad.lo.u32 " YC ", v, 2, nS;\n\t"                                                  \
@@ -250,13 +274,13 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
                  "selp.u32 k, 1, 0, one;\n\t"                                           \
                  "or.b32 %4, t, k;\n\t"                                                 \
                  "bra.uni F2_LIT_END;\n\t"                                              \
-                 F2_MIS("F2_MIS0", "yb", "q0", "yc", "F2_PL1")                          \
-                 F2_MIS("F2_MIS1", "yc", "q1", "ya", "F2_PL2")                          \
-                 F2_MIS("F2_MIS2", "ya", "q0", "yb", "F2_PL3")                          \
-                 F2_MIS("F2_MIS3", "yb", "q1", "yc", "F2_PL4")                          \
-                 F2_MIS("F2_MIS4", "yc", "q0", "ya", "F2_PL5")                          \
-                 F2_MIS("F2_MIS5", "ya", "q1", "yb", "F2_PL6")                          \
-                 F2_MIS("F2_MIS6", "yb", "q0", "yc", "F2_PL7")                          \
+                 F2_MIS("F2_MIS0", "yb", "q0", "yc", "F2_PL1", "pz")                        \
+                 F2_MIS("F2_MIS1", "yc", "q1", "ya", "F2_PL2", "p")                        \
+                 F2_MIS("F2_MIS2", "ya", "q0", "yb", "F2_PL3", "pz")                        \
+                 F2_MIS("F2_MIS3", "yb", "q1", "yc", "F2_PL4", "p")                        \
+                 F2_MIS("F2_MIS4", "yc", "q0", "ya", "F2_PL5", "pz")                        \
+                 F2_MIS("F2_MIS5", "ya", "q1", "yb", "F2_PL6", "p")                        \
+                 F2_MIS("F2_MIS6", "yb", "q0", "yc", "F2_PL7", "pz")                        \
                  "F2_LIT_END:\n\t}"                                                     \
                  : F2_IO(d), "=&r"(OUT) : "r"(S), "r"(MB), "r"(MATCHED) : "memory")
 
@@ -267,6 +291,30 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
                  "mad.lo.u32 %1, %1, 256, %2;\n\t"                                      \
                  "ld.shared.u8 %2, [%3];"                                               \
                  : F2_IO(d) : : "memory")
+
+// eight equiprobable bits between two normalisations: thresholds R >> 1 .. R >> 8, result MSB first
+#define F2_DSTEP(J, M)                                                                  \
+    "shr.u32 rj, %2, " J ";\n\t"                                                        \
+    "setp.ge.u32 one, %0, rj;\n\t"                                                      \
+    "@one sub.u32 %0, %0, rj;\n\t"                                                      \
+    "@one or.b32 %1, %1, " M ";\n\t"
+#define F2_DIRECT8(CODE, ACC, R)                                                        \
+    asm("{\n\t.reg .pred one;\n\t.reg .b32 rj;\n\tmov.u32 %1, 0;\n\t"                   \
+        F2_DSTEP("1", "128") F2_DSTEP("2", "64") F2_DSTEP("3", "32") F2_DSTEP("4", "16") \
+        F2_DSTEP("5", "8") F2_DSTEP("6", "4") F2_DSTEP("7", "2") F2_DSTEP("8", "1") "}"  \
+        : "+r"(CODE), "=&r"(ACC) : "r"(R))
+// the first K (< 8) of those steps only
+#define F2_DSTEP_IF(J, M)                                                               \
+    "setp.le.u32 live, " J ", %3;\n\t"                                                  \
+    "shr.u32 rj, %2, " J ";\n\t"                                                        \
+    "setp.ge.and.u32 one, %0, rj, live;\n\t"                                            \
+    "@one sub.u32 %0, %0, rj;\n\t"                                                      \
+    "@one or.b32 %1, %1, " M ";\n\t"
+#define F2_DIRECT_PART(CODE, ACC, R, K)                                                 \
+    asm("{\n\t.reg .pred one, live;\n\t.reg .b32 rj;\n\tmov.u32 %1, 0;\n\t"             \
+        F2_DSTEP("1", "128") F2_DSTEP_IF("2", "64") F2_DSTEP_IF("3", "32") F2_DSTEP_IF("4", "16") \
+        F2_DSTEP_IF("5", "8") F2_DSTEP_IF("6", "4") F2_DSTEP_IF("7", "2") "}"             \
+        : "+r"(CODE), "=&r"(ACC) : "r"(R), "r"(K))
 
 #define F2_FAIL(ST, SITE) do { d.status = (ST); d.site = (SITE); return OP_DONE; } while (0)
 
@@ -330,10 +378,10 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t 
         uint32_t len;
         const uint32_t state2 = (a_im - sP - 2u * P_IS_MATCH) >> 1;   // of THIS symbol (isRep0Long, :716)
         const uint32_t a_rep_cur = a_rep, pos_state_cur = pos_state;
-        F2_BIT(d, p_rep, a_rep, bit);                             // isRep, :195-213
-        if (LZ_LIKELY(bit == 0)) {  // simple match, :215-668
+        // isRep (:195-213) and, for a simple match, its length (:218-429) in one block
+        F2_ISREP_LEN(d, len, sP + 2u * P_LEN0, sP + 2u * (P_LEN0 + LEN_LOW) + 16u * pos_state_cur, a_rep, p_rep);
+        if (LZ_LIKELY(len != 0xFFFFFFFFu)) {  // simple match, :215-668
             d.rep3 = d.rep2; d.rep2 = d.rep1; d.rep1 = d.rep0;    // :216
-            F2_LEN(d, len, sP + 2u * P_LEN0, sP + 2u * (P_LEN0 + LEN_LOW) + 16u * pos_state_cur);   // :218-429
             d.state = d.state < 7 ? 7 : 10;                       // stateUpdateMatch, :431
             const uint32_t len_state = len > 3 ? 3 : len;         // :434-437
             len += 2;                                             // :656
@@ -368,32 +416,33 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t 
                     // the align tree's root and its children: in flight during the direct bits
                     const uint32_t al0 = f2_lds16(sP + 2u * P_ALIGN + 2), al2 = f2_lds16(sP + 2u * P_ALIGN + 4),
                                    al3 = f2_lds16(sP + 2u * P_ALIGN + 6);
-                    // DecodeDirectBits: as in decode_run (runs of halvings between normalisations)
-                    uint32_t res = 0;
+                    // DecodeDirectBits (:549-576) normalises when the halved range drops below 2^24: first
+                    // after g = 8 - clz(range) halvings, then after every 8th.  Between two normalisations
+                    // step j compares against range >> j, so only `code` is carried (4 instructions a bit).
+                    // The first run is made a full one: range < 2^(24+g), so range << (8-g) fits 32 bits and
+                    // its first 8-g thresholds (>= range > code) decide 0 and leave code alone.
+                    uint32_t res = 0, acc;
                     uint32_t n = nd - 4;                           // 1..26
-                    uint32_t g = 8 - LZ_CLZ(d.range);
+                    const uint32_t g = 8 - LZ_CLZ(d.range);        // 1..8
+                    if (LZ_LIKELY(n >= g)) {
+                        F2_DIRECT8(d.code, acc, d.range << (8 - g));
+                        res = acc;
+                        d.range >>= g;
+                        n -= g;
+                        F2_SHIFT8(d);
 #pragma unroll 1
-                    for (;;) {
-                        const uint32_t k = n < g ? n : g;
-                        const uint32_t r0 = d.range;
-                        uint32_t acc = 0;
-#pragma unroll
-                        for (uint32_t j = 1; j <= 8; j++) {
-                            asm("{\n\t.reg .pred live, one;\n\t.reg .b32 rj;\n\t"
-                                "setp.le.u32 live, %3, %4;\n\t"
-                                "shr.u32 rj, %2, %3;\n\t"
-                                "setp.ge.and.u32 one, %0, rj, live;\n\t"
-                                "@one sub.u32 %0, %0, rj;\n\t"
-                                "@one or.b32 %1, %1, %5;\n\t}"
-                                : "+r"(d.code), "+r"(acc)
-                                : "r"(r0), "r"(j), "r"(k), "r"(1u << (8 - j)));
+                        while (n >= 8) {
+                            F2_DIRECT8(d.code, acc, d.range);
+                            res = (res << 8) | acc;
+                            d.range >>= 8;
+                            n -= 8;
+                            F2_SHIFT8(d);
                         }
-                        d.range = r0 >> k;
-                        res = (res << k) | (acc >> (8 - k));
-                        n -= k;
-                        if (k == g) F2_SHIFT8(d);
-                        g = 8;
-                        if (n == 0) break;
+                    }
+                    if (n) {                                       // last run: n < 8 halvings, no normalisation after it
+                        F2_DIRECT_PART(d.code, acc, d.range, n);
+                        res = (res << n) | (acc >> (8 - n));
+                        d.range >>= n;
                     }
                     dist += res << 4;
                     uint32_t m;

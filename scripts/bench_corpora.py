@@ -60,5 +60,6 @@ if __name__ == "__main__":
         for n in (148, 592, 1024, 1924, 2048, 4096, 8192):
             run(ctx, "text", n, 1 << 20)
         run(ctx, "text", 2048, 4 << 20, distinct=16)      # BASELINE config 5's per-GPU shape at 8 GPUs
+        run(ctx, "random", 148, 1 << 20)
         run(ctx, "random", 1024, 1 << 20)
         run(ctx, "mixed", 1024, 1 << 20)
