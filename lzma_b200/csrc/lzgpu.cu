@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(32, 8) lzgpu_decode_kernel(const KArgs a) {
     io.out = a.out_base + u.out_off;
     io.out_cap = u.out_cap;
     io.stage = reinterpret_cast<uint8_t *>(smem_probs + a.stage_off);
-    io.inbuf = io.stage + 64;
+    io.inbuf = io.stage + 128;
     lzgpu_result &res = a.results[ui];
     if (u.kind == LZGPU_KIND_LZMA2_GROUP) run_unit_lzma2<kV>(u, io, P, L, a.lit_bits_cap, res);
     else run_unit_lzma1<kV>(u, io, P, L, res);
@@ -356,12 +356,12 @@ extern "C" void lzgpu_plan_destroy(lzgpu_plan *p) {
     delete p;
 }
 
-// shared memory of one unit: probability tables, 64 bytes of window-copy staging, the V_CHAIN input stage
+// shared memory of one unit: probability tables, 2 x 64 bytes of window-copy staging, the V_CHAIN input stage
 static size_t probs_elems(uint32_t lit_bits, bool lit_global) {
     return (size_t)P_FIXED + (lit_global ? 0 : ((size_t)0x300 << lit_bits));
 }
 static size_t smem_bytes(uint32_t lit_bits, bool lit_global) {
-    return sizeof(uint16_t) * probs_elems(lit_bits, lit_global) + 64 + kF2Stage;
+    return sizeof(uint16_t) * probs_elems(lit_bits, lit_global) + 128 + kF2Stage;
 }
 
 extern "C" int lzgpu_plan_create(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *units, int64_t n,

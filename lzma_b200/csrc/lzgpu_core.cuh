@@ -123,7 +123,7 @@ struct Dec {
     int32_t status, site;
     // V_CHAIN fast decoder (lzgpu_fast2.cuh): compressed input staged in shared memory, read a byte ahead
     uint32_t nb, ips, lims;         // next input byte (already loaded); its shared address; last address a symbol may start at
-    uint32_t sP, sL, sIn;           // shared-window addresses of the fixed tables, the literal tables, the input stage
+    uint32_t sP, sL, sIn, sStage;   // shared-window addresses of the fixed tables, the literal tables, the input stage, the copy stage
     const uint8_t *g0;              // global address of the byte staged at sIn
 };
 

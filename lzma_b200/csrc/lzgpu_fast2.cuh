@@ -117,6 +117,11 @@ namespace lzgpu {
 
 #define F2_IO(d) "+r"((d).range), "+r"((d).code), "+r"((d).nb), "+r"((d).ips)
 
+__device__ __forceinline__ uint32_t f2_lds8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
     uint32_t v;
     asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
@@ -243,7 +248,13 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
                  "ld.shared.u16 lo, [%5+4];\n\t"                                        \
                  "ld.shared.u16 hi, [%5+6];\n\t"                                        \
                  "add.u32 yb, %5, 4;\n\t"                                               \
-                 F2_L0("%5", F2_LD)                                                     \
+                 /* plain literal: one branch-free block, so that ptxas overlaps the levels */ \
+                 F2_L0("%5", F2_LD) F2_L1(F2_LD) F2_L2(F2_LD) F2_L3(F2_LD) F2_L4(F2_LD) F2_L5(F2_LD) F2_L6(F2_LD) F2_L7(F2_NOLD) \
+                 "add.u32 t, ya, nS;\n\t"                                               \
+                 "shr.u32 t, t, 2;\n\t"                                                 \
+                 "and.b32 %4, t, 255;\n\t"                                              \
+                 "bra.uni F2_LIT_END;\n\t"                                              \
+                 /* the same ladder with an entry per level, for a matched literal after its mismatch */ \
                  "F2_PL1:\n\t" F2_L1(F2_LD)                                             \
                  "F2_PL2:\n\t" F2_L2(F2_LD)                                             \
                  "F2_PL3:\n\t" F2_L3(F2_LD)                                             \
@@ -357,9 +368,16 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t 
 
         if (bit == 0) {  // literal, :44-175
             uint32_t prevb = d.prev_byte, matchb = d.mbyte;
-            if (d.ctx_pending) {                                 // first use of the last window copy's context loads
-                prevb = d.ctx_a;
-                matchb = d.ctx_b;
+            if (d.ctx_pending) {                                 // a window copy came right before
+                if (LZ_LIKELY(d.ctx_pending == 2)) {             // its source words are (being) staged in shared memory
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();                                //  other lanes' copies become visible
+                    prevb = f2_lds8(d.ctx_a);
+                    matchb = f2_lds8(d.ctx_b);
+                } else {
+                    prevb = d.ctx_a;
+                    matchb = d.ctx_b;
+                }
             }
             d.ctx_pending = 0;
             const uint32_t S = d.sL + 0x600u * (((d.wpos & d.lp_mask) << d.lc) + (prevb >> (8 - d.lc)));  // :56-57
@@ -525,19 +543,44 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t 
             out_dist = dist;
             return OP_COPY;
         }
-        // window.CopyMatch (window.go:55-87) for the common case: lane j moves byte j.  The previous
-        // match's bytes are stored first (they were held back so that nothing waited for their loads).
+        // window.CopyMatch (window.go:55-87) for the common case.  The source bytes (plus the byte after
+        // them, which a matched literal would need) are fetched by cp.async as the aligned 4-byte words
+        // that cover them, into one half of the copy stage; nothing waits for them here.  The PREVIOUS
+        // match's bytes are moved from the other half to the window first -- they were held back for the
+        // same reason.  (Loads into registers instead would keep a scoreboard busy across the loop, and
+        // ptxas then makes every following symbol wait for them at its first branch: measured, 86 cycles
+        // per symbol.)
         uint8_t *dst = d.outp;
-        F2_ST8_IF(wc.pend_dst + lane, wc.pend_val, lane, wc.pend_len);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
+        if (wc.pend_len) {
+            uint32_t v = 0;
+            if (wc.pend_staged) {
+                asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %2, %3;\n\t@q ld.shared.u8 %0, [%1];\n\t}"
+                             : "+r"(v) : "r"(d.sStage + wc.pend_off + lane), "r"(lane), "r"(wc.pend_len) : "memory");
+            } else {
+                v = wc.pend_val;                                  // left by the general copy code
+            }
+            F2_ST8_IF(wc.pend_dst + lane, v, lane, wc.pend_len);
+        }
+        __syncwarp();                                             // those stores precede the fetches below
         const uint8_t *src = dst - dist;
-        F2_LD8_IF(wc.pend_val, src + lane, lane, len);
-        LZ_LD_WIN8(d.ctx_a, src + (len - 1));                     // context of a literal that may follow:
-        LZ_LD_WIN8(d.ctx_b, src + len);                           // last byte of the match, byte at -(rep0+1) after it
-        d.ctx_pending = 1;
+        const uint32_t off = (uint32_t)(uintptr_t)src & 3u;
+        const uint32_t nw = (off + len + 4) >> 2;                 // words covering src[0 .. len] (len + 1 bytes): <= 9
+        const uint32_t sbuf = d.sStage + wc.stage_sel;
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %2, %3;\n\t"
+                     "@q cp.async.ca.shared.global [%0], [%1], 4;\n\t"
+                     "cp.async.commit_group;\n\t}"
+                     : : "r"(sbuf + 4u * lane), "l"(src - off + 4u * lane), "r"(lane), "r"(nw) : "memory");
+        d.ctx_a = sbuf + off + len - 1;                           // context of a literal that may follow: last byte of
+        d.ctx_b = sbuf + off + len;                               // the match, byte at -(rep0+1) after it
+        d.ctx_pending = 2;
         wc.pend_len = len;
         wc.pend_dst = dst;
-        wc.pend_staged = 0;
+        wc.pend_staged = 1;
+        wc.pend_off = wc.stage_sel + off;
+        wc.pend_dist = 0xFFFFFFFFu;                               // not self-overlapping (general commit code)
+        wc.stage_sel ^= 64u;
         d.outp = dst + len;
     }
 #undef F2_NEXT_CTX

@@ -42,7 +42,8 @@ struct WarpCopy {
     uint32_t pend_staged;  // the bytes wait in `stage` (cp.async) rather than in pend_val
     uint32_t pend_off;     // staged: offset of the source's first byte in `stage`
     uint32_t pend_dist;    // staged: match distance (period of an overlapping copy)
-    uint8_t *stage;        // 64-byte shared staging buffer of the warp (V_STAGE)
+    uint8_t *stage;        // shared staging buffer of the warp: 2 x 64 bytes (V_STAGE uses the first, V_CHAIN alternates)
+    uint32_t stage_sel;    // V_CHAIN: which half the NEXT copy stages into (0 / 64)
     uint8_t *out_limit;    // end of the unit's output range (staging over-reads <= 3 bytes)
     LZ_LANEVAR(uint32_t, pend_val);   // the byte, in a 32-bit register
 };
@@ -89,13 +90,14 @@ LZ_DEV void coder_reset(Dec &d, uint16_t *P, uint16_t *L, uint32_t lit_bits) {
 }
 
 // V_CHAIN addresses its tables and the input stage through 32-bit shared-window addresses
-LZ_DEV void set_shared_addrs(Dec &d, uint16_t *P, uint8_t *inbuf) {
+LZ_DEV void set_shared_addrs(Dec &d, uint16_t *P, uint8_t *inbuf, uint8_t *stage) {
 #if defined(__CUDA_ARCH__)
     d.sP = (uint32_t)__cvta_generic_to_shared(P);
     d.sL = d.sP + 2u * P_LIT;
     d.sIn = (uint32_t)__cvta_generic_to_shared(inbuf);
+    d.sStage = (uint32_t)__cvta_generic_to_shared(stage);
 #else
-    d.sP = d.sL = d.sIn = 0;
+    d.sP = d.sL = d.sIn = d.sStage = 0;
 #endif
     d.nb = d.ips = d.lims = 0;
     d.g0 = nullptr;
@@ -135,6 +137,13 @@ LZ_DEV bool f2_enter(Dec &d, const uint8_t *gpos, uint8_t *inbuf) {
 }
 // ... and back: the careful decoder's lookahead starts empty at the next unconsumed byte
 LZ_DEV void f2_leave(Dec &d) {
+    if (d.ctx_pending == 2) {   // context bytes of the last window copy still in the copy stage: fetch them
+        LZ_CP_WAIT();
+        LZ_SYNC();
+        d.ctx_a = d.stage[d.ctx_a - d.sStage];
+        d.ctx_b = d.stage[d.ctx_b - d.sStage];
+        d.ctx_pending = 1;
+    }
     d.ip = d.g0 + (d.ips - d.sIn);
     d.inb_hi = d.inb_lo = 0;
     d.inbits = 0;
@@ -278,9 +287,10 @@ LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     wc.pend_staged = 0;
     wc.pend_off = wc.pend_dist = 0;
     wc.stage = io.stage;
+    wc.stage_sel = 0;
     wc.out_limit = io.out + io.out_cap;
     set_props(d, u.lc, u.lp, u.pb);
-    set_shared_addrs(d, P, io.inbuf);
+    set_shared_addrs(d, P, io.inbuf, io.stage);
     d.dict_size = u.dict_size;
     d.wpos = 0;
     d.full = 0;
@@ -324,9 +334,10 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     wc.pend_staged = 0;
     wc.pend_off = wc.pend_dist = 0;
     wc.stage = io.stage;
+    wc.stage_sel = 0;
     wc.out_limit = io.out + io.out_cap;
     set_props(d, u.lc, u.lp, u.pb);
-    set_shared_addrs(d, P, io.inbuf);
+    set_shared_addrs(d, P, io.inbuf, io.stage);
     d.dict_size = u.dict_size;
     d.wpos = 0;
     d.full = 0;

@@ -43,7 +43,7 @@ extern "C" int emu_decode_batch(const lzgpu_unit *units, int64_t n, const uint8_
         memset(&r, 0, sizeof r);
         r.status = LZGPU_NOT_RUN;
         uint16_t *P = probs.data(), *L = probs.data() + P_LIT;
-        alignas(16) uint8_t stage[64];
+        alignas(16) uint8_t stage[128];
         io.stage = stage;
         alignas(16) uint8_t inbuf[kF2Stage];
         io.inbuf = inbuf;
