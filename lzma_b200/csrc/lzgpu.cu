@@ -24,7 +24,7 @@
 using namespace lzgpu;
 
 #ifndef LZGPU_DEFAULT_VARIANT
-#define LZGPU_DEFAULT_VARIANT 1
+#define LZGPU_DEFAULT_VARIANT 33
 #endif
 
 // ------------------------------------------------------------------ kernel

@@ -343,6 +343,29 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
 // margin is used up (OP_SWITCH: the caller refills the stage or hands over to the careful decoder).
 template <int kV>
 __device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t &out_len, uint32_t &out_dist) {
+    // Every lane holds the same decoder state, but the compiler cannot know: whatever derives from a
+    // memory load counts as divergent, and each `if` below would get a convergence barrier (BSSY /
+    // BSYNC, ~15 cycles a branch, measured).  Passing the state through a shuffle from lane 0 once
+    // per entry makes it provably uniform; inside the loop it is only touched by asm blocks whose
+    // inputs are uniform, so every branch of the loop compiles to a plain uniform branch.
+#define F2_U32(x) (x) = __shfl_sync(0xffffffffu, (x), 0)
+#define F2_U64P(T, x)                                                                   \
+    do {                                                                                \
+        const uint64_t v_ = (uint64_t)(uintptr_t)(x);                                   \
+        const uint32_t lo_ = __shfl_sync(0xffffffffu, (uint32_t)v_, 0), hi_ = __shfl_sync(0xffffffffu, (uint32_t)(v_ >> 32), 0); \
+        (x) = (T)(uintptr_t)(((uint64_t)hi_ << 32) | lo_);                              \
+    } while (0)
+    F2_U32(d.range); F2_U32(d.code); F2_U32(d.nb); F2_U32(d.ips); F2_U32(d.lims);
+    F2_U32(d.sP); F2_U32(d.sL); F2_U32(d.sStage);
+    F2_U32(d.rep0); F2_U32(d.rep1); F2_U32(d.rep2); F2_U32(d.rep3); F2_U32(d.state);
+    F2_U32(d.wpos); F2_U32(d.dict_size); F2_U32(d.full);
+    F2_U32(d.size_defined); F2_U32(d.lc); F2_U32(d.lp_mask); F2_U32(d.pos_mask);
+    F2_U32(d.prev_byte); F2_U32(d.mbyte); F2_U32(d.ctx_a); F2_U32(d.ctx_b); F2_U32(d.ctx_pending);
+    F2_U64P(uint8_t *, d.outp); F2_U64P(uint8_t *, d.fast_out_end);
+    F2_U32(wc.pend_len); F2_U32(wc.pend_staged); F2_U32(wc.pend_off); F2_U32(wc.stage_sel);
+    F2_U64P(uint8_t *, wc.pend_dst);
+#undef F2_U32
+#undef F2_U64P
     const uint32_t sP = d.sP;
     const uint32_t lane = LZ_LANE();
     // the next symbol's isMatch / isRep probabilities are loaded as soon as the current symbol has fixed

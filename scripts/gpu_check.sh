@@ -1,11 +1,12 @@
 #!/bin/bash
-# Runs on the GPU box via gpurun: tests, smoke, bench, then ncu launch list + one full capture.
+# Runs on the GPU box via gpurun: tests, smoke, memcheck, bench (both arms), then ncu launch list + one full capture.
 mkdir -p gpurun_out
 { nproc; lscpu | grep -E "Model name|Socket|Core|Thread|^CPU\(s\)"; free -g | head -2; nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv; } > gpurun_out/box.txt 2>&1
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
 tail -3 gpurun_out/smoke.log
+timeout 600 compute-sanitizer --tool memcheck python scripts/sanitize_case.py > gpurun_out/sanitize_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/sanitize_memcheck.log
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json
@@ -16,4 +17,4 @@ python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/pla
 ncu --set full --clock-control none --import-source on -k regex:lzgpu_decode -s 3 -c 1 -o gpurun_out/prof -f python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
 fi
-ls -la gpurun_out
+ls -la gpurun_out | head -5
