@@ -39,6 +39,7 @@ struct KArgs {
     uint32_t lit_bits_cap;       // literal-table capacity of this launch, as lc+lp
     uint32_t slot0;              // first slot of this launch in `order`
     uint32_t stage_off;          // uint16 index of the 64-byte staging buffer inside the shared array
+    uint32_t *progress;          // per unit: decoded bytes that are final in HBM, in 64 KiB blocks (host-mapped; may be null)
 };
 
 // One warp per CTA, one unit per warp.  Fixed tables (3.7 KB) always in shared
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(32, 8) lzgpu_decode_kernel(const KArgs a) {
     io.out_cap = u.out_cap;
     io.stage = reinterpret_cast<uint8_t *>(smem_probs + a.stage_off);
     io.inbuf = io.stage + 128;
+    io.progress = a.progress ? a.progress + ui : nullptr;
     lzgpu_result &res = a.results[ui];
     if (u.kind == LZGPU_KIND_LZMA2_GROUP) run_unit_lzma2<kV>(u, io, P, L, a.lit_bits_cap, res);
     else run_unit_lzma1<kV>(u, io, P, L, res);
@@ -275,6 +277,10 @@ struct DevState {
     // grow-only staging for the host-buffer entry point
     uint8_t *d_in = nullptr, *d_out = nullptr;
     uint64_t in_cap = 0, out_cap = 0;
+    // streamed D2H: second stream, host-mapped progress counters (grow-only)
+    cudaStream_t copy_stream = nullptr;
+    uint32_t *h_progress = nullptr, *d_progress = nullptr;
+    uint64_t progress_cap = 0;
 };
 
 struct lzgpu_ctx {
@@ -303,6 +309,7 @@ struct lzgpu_plan {
     int32_t *d_order = nullptr;
     lzgpu_result *d_results = nullptr;
     uint16_t *d_lit_ws = nullptr;
+    uint32_t *d_progress = nullptr;       // optional, set by the host-buffer entry point
     uint64_t lit_ws_stride = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t last_stream = nullptr;
@@ -336,6 +343,8 @@ extern "C" void lzgpu_ctx_destroy(lzgpu_ctx *c) {
     for (auto &d : c->devs) {
         cudaSetDevice(d.device);
         if (d.stream) cudaStreamDestroy(d.stream);
+        if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
+        if (d.h_progress) cudaFreeHost(d.h_progress);
         if (d.d_in) cudaFree(d.d_in);
         if (d.d_out) cudaFree(d.d_out);
     }
@@ -480,6 +489,7 @@ extern "C" int lzgpu_plan_launch(lzgpu_plan *p, const uint8_t *d_in, uint8_t *d_
         a.lit_bits_cap = L.lit_bits;
         a.slot0 = L.slot0;
         a.stage_off = (uint32_t)probs_elems(L.lit_bits, L.lit_global);
+        a.progress = p->d_progress;
         if (L.lit_global) launch_decode<true>(p->variant, L.count, L.smem, st, a);
         else launch_decode<false>(p->variant, L.count, L.smem, st, a);
         CUDA_TRY(cudaGetLastError());
@@ -597,7 +607,8 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
         ir[k] = {sh.units[k].in_off, sh.units[k].in_len};
         orr[k] = {sh.units[k].out_off, sh.units[k].out_cap};
     }
-    std::vector<uint64_t> ioff, ooff;
+    std::vector<uint64_t> ioff, ooff, host_out_off(n);
+    for (size_t k = 0; k < n; k++) host_out_off[k] = sh.units[k].out_off;
     layout_ranges(ir, ioff, sh.in_runs, sh.in_bytes);
     layout_ranges(orr, ooff, sh.out_runs, sh.out_bytes);
     for (size_t k = 0; k < n; k++) { sh.units[k].in_off = ioff[k]; sh.units[k].out_off = ooff[k]; }
@@ -609,6 +620,33 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
     lzgpu_plan *plan = nullptr;
     int rc = lzgpu_plan_create(ctx, dev_index, sh.units.data(), (int64_t)n, sh.in_bytes + 16, sh.out_bytes + 16, &plan);
     if (rc != LZGPU_E_OK) { sh.rc = rc; sh.err = g_last_error; return; }
+    // Streamed D2H for large shards: the kernel publishes, per unit, how many 64 KiB blocks of its output
+    // are final (host-mapped counters); this thread polls them while the kernel runs and sends finished
+    // blocks to the caller's buffer on a second stream, so that only each unit's tail is left to copy
+    // when the kernel ends.  (LZGPU_NO_STREAM_D2H=1 restores kernel-then-copy.)
+    const uint64_t kBlock = 64 << 10;
+    bool stream_out = sh.out_bytes >= ((uint64_t)32 << 20) && !getenv("LZGPU_NO_STREAM_D2H");
+    if (stream_out) {
+        if (!ds.copy_stream && cudaStreamCreateWithFlags(&ds.copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); stream_out = false; }
+        if (stream_out && ds.progress_cap < n) {
+            if (ds.h_progress) cudaFreeHost(ds.h_progress);
+            ds.h_progress = nullptr; ds.d_progress = nullptr; ds.progress_cap = 0;
+            const size_t want = n + (n >> 2) + 64;
+            if (cudaHostAlloc(&ds.h_progress, want * sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess ||
+                cudaHostGetDevicePointer(&ds.d_progress, ds.h_progress, 0) != cudaSuccess) {
+                cudaGetLastError();
+                if (ds.h_progress) cudaFreeHost(ds.h_progress);
+                ds.h_progress = nullptr; ds.d_progress = nullptr;
+                stream_out = false;
+            } else {
+                ds.progress_cap = want;
+            }
+        }
+        if (stream_out) {
+            memset(ds.h_progress, 0, n * sizeof(uint32_t));
+            plan->d_progress = ds.d_progress;
+        }
+    }
     cudaEvent_t e0, e1, e2, e3;
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
     cudaEventRecord(e0, ds.stream);
@@ -622,6 +660,34 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
         if (rc != LZGPU_E_OK) { sh.rc = rc; sh.err = g_last_error; }
     }
     cudaEventRecord(e2, ds.stream);
+    if (sh.rc == 0 && stream_out) {
+        std::vector<uint32_t> copied(n, 0);
+        volatile const uint32_t *prog = ds.h_progress;
+        auto send = [&](size_t k, uint64_t from, uint64_t to) {   // bytes [from, to) of unit k's output
+            if (to <= from || sh.rc != 0) return;
+            cudaError_t ce = cudaMemcpyAsync(out_base + host_out_off[k] + from, ds.d_out + sh.units[k].out_off + from, to - from,
+                                             cudaMemcpyDeviceToHost, ds.copy_stream);
+            if (ce != cudaSuccess) cuda_fail(ce, "D2H (streamed)");
+        };
+        for (;;) {
+            const cudaError_t q = cudaEventQuery(e2);
+            if (q != cudaErrorNotReady) { if (q != cudaSuccess) cuda_fail(q, "decode kernel"); break; }
+            for (size_t k = 0; k < n && sh.rc == 0; k++) {
+                const uint32_t have = prog[k];
+                if (have > copied[k]) {
+                    const uint64_t cap = sh.units[k].out_cap;
+                    send(k, std::min<uint64_t>(copied[k] * kBlock, cap), std::min<uint64_t>(have * kBlock, cap));
+                    copied[k] = have;
+                }
+            }
+            if (sh.rc != 0) break;
+        }
+        for (size_t k = 0; k < n && sh.rc == 0; k++)           // the tails
+            send(k, std::min<uint64_t>(copied[k] * kBlock, sh.units[k].out_cap), sh.units[k].out_cap);
+        cudaEventRecord(e3, ds.copy_stream);
+        e = cudaStreamSynchronize(ds.copy_stream);
+        if (e != cudaSuccess && sh.rc == 0) cuda_fail(e, "D2H (streamed) sync");
+    } else {
     if (sh.rc == 0) {
         for (const auto &r : sh.out_runs) {
             e = cudaMemcpyAsync(out_base + r.host_off, ds.d_out + r.dev_off, r.len, cudaMemcpyDeviceToHost, ds.stream);
@@ -629,6 +695,7 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
         }
     }
     cudaEventRecord(e3, ds.stream);
+    }
     e = cudaStreamSynchronize(ds.stream);
     if (e != cudaSuccess && sh.rc == 0) cuda_fail(e, "decode kernel / stream sync");
     if (sh.rc == 0) {

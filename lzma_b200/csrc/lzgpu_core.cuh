@@ -125,6 +125,10 @@ struct Dec {
     uint32_t nb, ips, lims;         // next input byte (already loaded); its shared address; last address a symbol may start at
     uint32_t sP, sL, sIn, sStage;   // shared-window addresses of the fixed tables, the literal tables, the input stage, the copy stage
     const uint8_t *g0;              // global address of the byte staged at sIn
+    // streamed D2H (host-buffer entry point): decoded bytes that are final, published in 64 KiB blocks
+    uint32_t *prog;                 // host-mapped counter of this unit, or null
+    const uint8_t *out0;            // start of the unit's output
+    uint32_t pub;                   // blocks published so far
 };
 
 // Input is consumed through a 64-bit lookahead register so that the per-bit

@@ -135,6 +135,22 @@ LZ_DEV bool f2_enter(Dec &d, const uint8_t *gpos, uint8_t *inbuf) {
     return false;
 #endif
 }
+// Streamed D2H: tell the host how much of this unit's output is final (stored and never touched again),
+// in 64 KiB blocks.  Called from the stage-refill path only (every few hundred input bytes).
+LZ_DEV void publish_progress(Dec &d, const WarpCopy &wc) {
+#if defined(__CUDA_ARCH__)
+    if (d.prog) {
+        const uint8_t *fin = wc.pend_len ? wc.pend_dst : d.outp;   // a pending window copy is not stored yet
+        const uint32_t blocks = (uint32_t)((uint64_t)(fin - d.out0) >> 16);
+        if (blocks != d.pub) {
+            __threadfence_system();      // every lane: its window stores are visible before the counter is
+            __syncwarp();
+            if (LZ_LANE() == 0) *(volatile uint32_t *)d.prog = blocks;
+            d.pub = blocks;
+        }
+    }
+#endif
+}
 // ... and back: the careful decoder's lookahead starts empty at the next unconsumed byte
 LZ_DEV void f2_leave(Dec &d) {
     if (d.ctx_pending == 2) {   // context bytes of the last window copy still in the copy stage: fetch them
@@ -166,6 +182,7 @@ LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8
                     op = decode_fast2<kV>(d, wc, len, dist);
                     if (op != OP_SWITCH) break;
                     // stage used up (refill) or the unit's tail reached (careful decoder from here on)
+                    publish_progress(d, wc);
                     if (d.outp <= d.fast_out_end && f2_enter<kV>(d, d.g0 + (d.ips - d.sIn), inbuf)) continue;
                     f2_leave(d);
                     fast = false;
@@ -274,6 +291,7 @@ struct UnitIO {
     uint64_t out_cap;
     uint8_t *stage;          // 64 bytes of shared memory, 4-byte aligned (window-copy staging)
     uint8_t *inbuf;          // kF2Stage bytes of shared memory, 16-byte aligned (V_CHAIN input stage)
+    uint32_t *progress;      // host-mapped progress counter of this unit (streamed D2H), or null
 };
 
 // LZMA1 unit (kind RAW; ALONE units are converted by the host).
@@ -291,6 +309,9 @@ LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     wc.out_limit = io.out + io.out_cap;
     set_props(d, u.lc, u.lp, u.pb);
     set_shared_addrs(d, P, io.inbuf, io.stage);
+    d.prog = io.progress;
+    d.out0 = io.out;
+    d.pub = 0;
     d.dict_size = u.dict_size;
     d.wpos = 0;
     d.full = 0;
@@ -338,6 +359,9 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     wc.out_limit = io.out + io.out_cap;
     set_props(d, u.lc, u.lp, u.pb);
     set_shared_addrs(d, P, io.inbuf, io.stage);
+    d.prog = io.progress;
+    d.out0 = io.out;
+    d.pub = 0;
     d.dict_size = u.dict_size;
     d.wpos = 0;
     d.full = 0;

@@ -47,6 +47,7 @@ extern "C" int emu_decode_batch(const lzgpu_unit *units, int64_t n, const uint8_
         io.stage = stage;
         alignas(16) uint8_t inbuf[kF2Stage];
         io.inbuf = inbuf;
+        io.progress = nullptr;
         switch (variant) {
             case 0: run_one<0>(u, io, P, L, bits, r); break;
             case 5: run_one<5>(u, io, P, L, bits, r); break;
