@@ -391,21 +391,20 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t 
 
         if (bit == 0) {  // literal, :44-175
             uint32_t prevb = d.prev_byte, matchb = d.mbyte;
-            if (d.ctx_pending) {                                 // a window copy came right before
-                if (LZ_LIKELY(d.ctx_pending == 2)) {             // its source words are (being) staged in shared memory
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
-                    __syncwarp();                                //  other lanes' copies become visible
-                    prevb = f2_lds8(d.ctx_a);
-                    matchb = f2_lds8(d.ctx_b);
-                } else {
-                    prevb = d.ctx_a;
-                    matchb = d.ctx_b;
-                }
+            if (d.ctx_pending) {                                 // a window copy came right before: its source
+                asm volatile("cp.async.wait_group 0;" ::: "memory");   // words are (being) staged in shared memory
+                __syncwarp();                                    //  other lanes' copies become visible
+                prevb = f2_lds8(d.ctx_a);
+                matchb = f2_lds8(d.ctx_b);
             }
             d.ctx_pending = 0;
             const uint32_t S = d.sL + 0x600u * (((d.wpos & d.lp_mask) << d.lc) + (prevb >> (8 - d.lc)));  // :56-57
             const uint32_t matched = d.state >= 7 ? 1u : 0u;
-            d.state = d.state < 4 ? 0 : (d.state < 10 ? d.state - 3 : d.state - 6);  // stateUpdateLiteral
+            {                                                    // stateUpdateLiteral (state.go:153-163), branch-free
+                uint32_t ns = (d.state > 3u ? d.state : 3u) - 3u;
+                if (d.state >= 10u) ns -= 3u;
+                d.state = ns;
+            }
             d.wpos++;
             if (LZ_UNLIKELY(d.wpos >= d.dict_size)) { d.wpos -= d.dict_size; d.full = 1; }
             F2_NEXT_CTX();
@@ -576,14 +575,10 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t 
         uint8_t *dst = d.outp;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
-        if (wc.pend_len) {
+        {   // (a pending copy is always a staged one here: the general copy code does not defer for this decoder)
             uint32_t v = 0;
-            if (wc.pend_staged) {
-                asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %2, %3;\n\t@q ld.shared.u8 %0, [%1];\n\t}"
-                             : "+r"(v) : "r"(d.sStage + wc.pend_off + lane), "r"(lane), "r"(wc.pend_len) : "memory");
-            } else {
-                v = wc.pend_val;                                  // left by the general copy code
-            }
+            asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %2, %3;\n\t@q ld.shared.u8 %0, [%1];\n\t}"
+                         : "+r"(v) : "r"(d.sStage + wc.pend_off + lane), "r"(lane), "r"(wc.pend_len) : "memory");
             F2_ST8_IF(wc.pend_dst + lane, v, lane, wc.pend_len);
         }
         __syncwarp();                                             // those stores precede the fetches below

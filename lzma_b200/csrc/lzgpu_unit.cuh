@@ -125,6 +125,11 @@ LZ_DEV bool f2_enter(Dec &d, const uint8_t *gpos, uint8_t *inbuf) {
     }
     if (l < 4 && g0 + kF2Stage + 128u * l < d.in_end) LZ_PREFETCH_L2(g0 + kF2Stage + 128u * l);
     __syncwarp();
+    if (d.ctx_pending == 1) {   // context bytes held as values (careful decoder's convention): fold them in
+        d.prev_byte = d.ctx_a;
+        d.mbyte = d.ctx_b;
+        d.ctx_pending = 0;
+    }
     const uint32_t off = (uint32_t)(gpos - g0);
     d.g0 = g0;
     d.ips = d.sIn + off;
@@ -237,6 +242,17 @@ LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8
                 d.ctx_a = off + (far ? len - 1 : src_index(len - 1, dist));
                 d.ctx_b = off + (far ? len : src_index(len, dist));
                 d.ctx_pending = 2;
+            } else if (kV & V_CHAIN) {
+                // This decoder does its common copies itself (lzgpu_fast2.cuh); what arrives here is rare
+                // (longer than 32 bytes, self-overlapping, or at the head / tail of a unit): copied at once,
+                // the context of a following literal read back from the window.
+                LZ_FOR_LANES(l) {
+                    for (uint32_t i = l; i < len; i += 32) dst[i] = src[far ? i : src_index(i, dist)];
+                }
+                LZ_SYNC();
+                d.prev_byte = dst[len - 1];
+                d.mbyte = dst[(int64_t)len - (int64_t)dist];
+                d.ctx_pending = 0;
             } else {
                 if (len <= 32) {
                     // deferred in registers: load now, store at the next commit
