@@ -215,6 +215,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device; lzma_b200 has no CPU decode path")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL prints its version banner to STDOUT when NCCL_DEBUG asks for it; stdout carries the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("LZGPU_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
