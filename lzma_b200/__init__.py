@@ -10,6 +10,7 @@ toolchain is absent here -- the cgo binding a maintainer adds is in INTEGRATION.
   DecodeProp, DecodeDictSize, DecodeUnpackSize, DecodeDictSize2
   Err* (errors.go)                              errors.Err*, errors.Is
   (new) batch entry point                       batch.Context.decode_batch / lzgpu_decode_batch
+  (new) .xz container front-end                 xz.decode_xz / xz.decode_xz_files (all blocks in one batch)
 
 All decoding happens in liblzgpu.so on the GPU; importing the decode entry points without the
 built library, or calling them without a CUDA device, fails loudly.
@@ -25,6 +26,7 @@ _LAZY = {
     "NewReader2": "reader2", "Reader2": "reader2", "NewLZMA2DecompressorForSevenZip": "reader2",
     "DecodeDictSize2": "reader2", "Context": "batch", "Plan": "batch", "decode_alone_streams": "batch",
     "decode_lzma2_stream": "batch", "scan_lzma2": "batch", "shard_units": "batch",
+    "decode_xz": "xz", "decode_xz_files": "xz", "scan_xz": "xz",
 }
 
 

@@ -51,6 +51,41 @@ def run(ctx, kind, n_units, size, distinct=32, steps=3):
                       "ms": round(ms, 2), "GBps": round(n_units * size / ms / 1e6, 3)}), flush=True)
 
 
+def run_lzma2(ctx, n_blocks, size, distinct=32, steps=3):
+    """BASELINE config 3: ONE raw LZMA2 stream with a dictionary reset every `size` bytes; the host scanner
+    cuts it into units (chunk runs starting at a dictionary reset) that decode in parallel."""
+    blocks = [K.text_block(2000 + i, size) for i in range(distinct)]
+    parts = [K.compress_raw_lzma2(b) for b in blocks]
+    seq = [i % distinct for i in range(n_blocks)]
+    stream = b"".join(parts[i][:-1] for i in seq[:-1]) + parts[seq[-1]]
+    units, total, sst = B.scan_lzma2(stream, 8 << 20)
+    assert len(units) == n_blocks and total == n_blocks * size and sst == L.OK
+    in_buf = np.frombuffer(stream + bytes(16), dtype=np.uint8)
+    d_in = torch.from_numpy(in_buf.copy()).cuda()
+    d_out = torch.empty(total + 16, dtype=torch.uint8, device="cuda")
+    plan = ctx.plan(units, in_buf.nbytes, total + 16)
+    st = torch.cuda.current_stream().cuda_stream or 1
+    for _ in range(2):
+        plan.launch(d_in.data_ptr(), d_out.data_ptr(), st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        plan.launch(d_in.data_ptr(), d_out.data_ptr(), st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    res, _ = plan.results()
+    out = d_out.cpu().numpy()
+    crcs = [zlib.crc32(b) for b in blocks]
+    for k in range(0, n_blocks, max(1, n_blocks // 64)):
+        assert res[k].status == L.OK and zlib.crc32(out[k * size:(k + 1) * size]) == crcs[seq[k]]
+    plan.close()
+    del d_in, d_out
+    print(json.dumps({"kind": "lzma2-stream", "units": n_blocks, "unit_bytes": size, "ratio": round(total / len(stream), 2),
+                      "ms": round(ms, 2), "GBps": round(total / ms / 1e6, 3)}), flush=True)
+
+
 if __name__ == "__main__":
     with B.Context([0]) as ctx:
         if "--quick" in sys.argv:          # A/B of tuning variants: lone-warp latency and the bench shape
@@ -63,3 +98,4 @@ if __name__ == "__main__":
         run(ctx, "random", 148, 1 << 20)
         run(ctx, "random", 1024, 1 << 20)
         run(ctx, "mixed", 1024, 1 << 20)
+        run_lzma2(ctx, 1024, 1 << 20)                     # BASELINE config 3: one 1 GiB LZMA2 stream
