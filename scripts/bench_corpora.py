@@ -2,6 +2,7 @@
 """Device-timed throughput of the decode kernel on other shapes than bench.py's headline workload:
 batch size (units per GPU), unit size, and data kind.  Inputs resident in HBM, CUDA events around
 the launches, every unit's CRC checked.  Prints one JSON line per shape."""
+import ctypes as C
 import json
 import os
 import sys
@@ -51,6 +52,47 @@ def run(ctx, kind, n_units, size, distinct=32, steps=3):
                       "ms": round(ms, 2), "GBps": round(n_units * size / ms / 1e6, 3)}), flush=True)
 
 
+def run_replicated(ctx, n_units, size, distinct=16, steps=2):
+    """BASELINE config 5 on ONE GPU (16 384 streams x 4 MiB = 64 GiB of output): `distinct` compressed streams are
+    resident once and every unit decodes one of them into its OWN output range, so the kernel does the full work
+    while the host builds only `distinct` streams.  A sample of units is copied back and CRC-checked."""
+    plains = [K.text_block(3000 + i, size) for i in range(distinct)]
+    streams = [K.compress_alone(p) for p in plains]
+    t_units, in_buf, _, _ = B.build_alone_batch(streams, [size] * distinct)
+    units = (L.Unit * n_units)()
+    for k in range(n_units):
+        t = t_units[k % distinct]
+        u = units[k]
+        C.memmove(C.byref(u), C.byref(t), C.sizeof(L.Unit))
+        u.out_off = k * size
+        u.out_cap = size
+    out_size = n_units * size + 16
+    d_in = torch.from_numpy(in_buf).cuda()
+    d_out = torch.empty(out_size, dtype=torch.uint8, device="cuda")
+    plan = ctx.plan(units, in_buf.nbytes, out_size)
+    st = torch.cuda.current_stream().cuda_stream or 1
+    plan.launch(d_in.data_ptr(), d_out.data_ptr(), st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        plan.launch(d_in.data_ptr(), d_out.data_ptr(), st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    res, _ = plan.results()
+    bad = sum(1 for k in range(n_units) if res[k].status != L.OK or res[k].bytes_out != size)
+    assert bad == 0, bad
+    crcs = [zlib.crc32(p) for p in plains]
+    for k in range(0, n_units, max(1, n_units // 96)):
+        assert zlib.crc32(d_out[k * size:(k + 1) * size].cpu().numpy()) == crcs[k % distinct], k
+    comp = sum(len(streams[k % distinct]) for k in range(n_units))
+    plan.close()
+    del d_in, d_out
+    print(json.dumps({"kind": "text-replicated", "units": n_units, "unit_bytes": size, "distinct": distinct,
+                      "ratio": round(n_units * size / comp, 2), "ms": round(ms, 2), "GBps": round(n_units * size / ms / 1e6, 3)}), flush=True)
+
+
 def run_lzma2(ctx, n_blocks, size, distinct=32, steps=3):
     """BASELINE config 3: ONE raw LZMA2 stream with a dictionary reset every `size` bytes; the host scanner
     cuts it into units (chunk runs starting at a dictionary reset) that decode in parallel."""
@@ -88,6 +130,9 @@ def run_lzma2(ctx, n_blocks, size, distinct=32, steps=3):
 
 if __name__ == "__main__":
     with B.Context([0]) as ctx:
+        if "--config5" in sys.argv:        # 16 384 x 4 MiB on one GPU (64 GiB of output in HBM)
+            run_replicated(ctx, 16384, 4 << 20)
+            sys.exit(0)
         if "--quick" in sys.argv:          # A/B of tuning variants: lone-warp latency and the bench shape
             for n in (148, 1024):
                 run(ctx, "text", n, 1 << 20)
