@@ -1,8 +1,12 @@
 """Host-side mirror of reader2.go: the raw-LZMA2 reader API over the GPU batch engine.
 
-NewReader2 reads the first chunk header eagerly like the reference (reader2.go:26-41,77-98);
-the first Read scans the whole stream into units (chunk runs that begin at a dictionary
-reset) and decodes them in parallel on the GPU(s)."""
+NewReader2 reads the first chunk header eagerly like the reference (reader2.go:26-41,77-98).
+Read then works in WAVES: the input is read incrementally, chunk headers are
+walked on the host (reader2.go:100-214) until enough units -- chunk runs that begin at a dictionary
+reset -- are buffered (`wave_bytes` of decoded output), that wave is decoded in parallel on the
+GPU(s) and served; the next wave is read and decoded when the previous one has been delivered.
+Memory is bounded by the wave size (unless the stream never resets its dictionary), and a caller
+that stops reading early never pays for the rest of the stream."""
 from __future__ import annotations
 
 import numpy as np
@@ -28,6 +32,11 @@ class Reader2:
         self._out = None
         self._pos = 0
         self._err = None
+        self._buf = None
+        self._rd = 0
+        self._in_eof = False
+        self._last = False
+        self.wave_bytes = 256 << 20          # decoded bytes per GPU call (at least one unit)
 
     def _initialize(self):
         """validateDictSize + startChunk (reader2.go:77-173) as far as the first header."""
@@ -58,22 +67,98 @@ class Reader2:
                 return E.Errorf("rangeDec.Init", E.ErrResultError)
         return None
 
-    def _decode(self):
-        data = self._head + self._in.read()
+    # ---- incremental input ----
+    def _fill(self, need: int) -> bool:
+        """Make at least `need` unread bytes available in self._buf (False: the input ended first)."""
+        while len(self._buf) - self._rd < need and not self._in_eof:
+            c = self._in.read(max(1 << 20, need - (len(self._buf) - self._rd)))
+            if not c:
+                self._in_eof = True
+                break
+            self._buf += c
+        return len(self._buf) - self._rd >= need
+
+    def _independent_from(self, pos: int) -> bool:
+        """Uncompressed chunk with dictionary reset at `pos`: does the first LZMA chunk after it (if any comes
+        before the next reset) reset the state and carry properties?  Otherwise it inherits the previous
+        unit's coder (reader2.go:155-165) and must stay in the same wave."""
+        buf, p0 = self._buf, pos
+        while True:
+            self._rd = p0                                       # _fill counts from the wave's read position
+            if not self._fill(pos - p0 + 3):
+                return True
+            c = buf[pos]
+            if c == 0 or 3 <= c < 0x80 or c >= 0xE0 or (c == 1 and pos != p0):
+                return True
+            if c >= 0x80:
+                return c >= 0xC0
+            pos += 3 + ((buf[pos + 1] << 8) | buf[pos + 2]) + 1
+
+    def _next_wave(self):
+        """Walk chunk headers from the current position until `wave_bytes` of output are covered and
+        the next chunk starts a new unit (dictionary reset).  Returns (bytes of the wave, last)."""
+        buf = self._buf
+        start = pos = self._rd
+        out = 0
+        first = True
+        while True:
+            self._rd = pos
+            if not self._fill(1):
+                return bytes(buf[start:]), True                 # ran off the input: the scanner reports it
+            ctrl = buf[pos]
+            if ctrl == 0 or 3 <= ctrl < 0x80:                   # end of stream (0x03-0x7F too: Q6)
+                self._rd = pos + 1
+                return bytes(buf[start:pos + 1]), True
+            # a unit that inherits nothing: dictionary reset AND the first LZMA chunk after it brings new properties
+            reset = ctrl >= 0xE0 or (ctrl == 1 and not first and out >= self.wave_bytes and self._independent_from(pos))
+            if reset and not first and out >= self.wave_bytes:
+                return bytes(buf[start:pos]) + b"\0", False     # wave ends before this chunk; terminate it
+            hl = 3 if ctrl < 0x80 else (5 if ctrl < 0xC0 else 6)
+            if not self._fill(hl):
+                self._rd = len(buf)
+                return bytes(buf[start:]), True
+            usz = ((buf[pos + 1] << 8) | buf[pos + 2]) + 1
+            if ctrl >= 0x80:
+                usz += (ctrl & 0x1F) << 16
+                payload = ((buf[pos + 3] << 8) | buf[pos + 4]) + 1
+            else:
+                payload = usz
+            if not self._fill(hl + payload):
+                self._rd = len(buf)
+                return bytes(buf[start:]), True
+            pos += hl + payload
+            out += usz
+            first = False
+
+    def _decode_wave(self):
+        if self._buf is None:                                   # first wave: header bytes read by NewReader2
+            self._buf = bytearray(self._head)
+            self._rd = 0
+            self._in_eof = False
+        data, last = self._next_wave()
+        if self._rd > (8 << 20):                                # drop what has been handed to the GPU
+            del self._buf[:self._rd]
+            self._rd = 0
         ctx = self._ctx or default_context()
         st, _site, out = B.decode_lzma2_stream(ctx, data, self._dict)
         self._out = np.frombuffer(out, dtype=np.uint8)
+        self._pos = 0
         self._err = _status_error(st)
+        self._last = last or self._err is not None
 
     def Read(self, p) -> tuple:
         """reader2.go:216-250."""
         if self._out is None:
-            self._decode()
+            self._decode_wave()
+        while self._pos == len(self._out) and not self._last and len(p):
+            self._decode_wave()                                 # previous wave delivered: next one
         n = min(len(p), len(self._out) - self._pos)
         if n:
             p[:n] = self._out[self._pos:self._pos + n].tobytes()
             self._pos += n
         if n == len(p) and n > 0:
+            return n, None
+        if not self._last:
             return n, None
         if self._err is not None:
             err, self._err = self._err, None

@@ -121,6 +121,44 @@ def test_lzma2_reader_multi_unit_and_truncation(ctx):
     assert err is E.ErrUnexpectedEOF and b"".join(blocks).startswith(sink.getvalue())
 
 
+class _CountingIO(io.BytesIO):
+    bytes_read = 0
+
+    def read(self, n=-1):
+        c = super().read(n)
+        self.bytes_read += len(c)
+        return c
+
+
+def test_lzma2_reader_waves(ctx):
+    """Read in waves: bounded look-ahead, same bytes, same errors, early stop reads only a prefix."""
+    blocks = [K.text_block(20 + i, 150_000) for i in range(6)]
+    s = K.lzma2_with_resets(blocks, dict_size=1 << 20)
+    plain = b"".join(blocks)
+    for wave in (1, 200_000, 10 << 20):
+        src = _CountingIO(s)
+        r, err = NewReader2(src, 1 << 20, ctx)
+        assert err is None
+        r.wave_bytes = wave
+        sink = io.BytesIO()
+        n, err = lzma.io_copy(sink, r)
+        assert err is None and sink.getvalue() == plain, wave
+    # early stop: only the first wave's input (and the read-ahead block) has been consumed
+    big = K.lzma2_with_resets([K.random_block(40 + i, 700_000) for i in range(6)], dict_size=1 << 20)
+    src = _CountingIO(big)
+    r, err = NewReader2(src, 1 << 20, ctx)
+    r.wave_bytes = 1
+    buf = bytearray(1000)
+    assert r.Read(buf)[0] == 1000
+    assert src.bytes_read < len(big) // 2
+    # truncation inside a later wave
+    r, err = NewReader2(io.BytesIO(s[:len(s) - 30_000]), 1 << 20, ctx)
+    r.wave_bytes = 1
+    sink = io.BytesIO()
+    n, err = lzma.io_copy(sink, r)
+    assert err is E.ErrUnexpectedEOF and plain.startswith(sink.getvalue()) and n > 4 * 150_000
+
+
 class _Closer(io.BytesIO):
     closed_calls = 0
 
