@@ -19,12 +19,32 @@
 #if defined(__CUDA_ARCH__)
 #define LZ_LANE() (threadIdx.x & 31u)
 #define LZ_FOR_LANES(l) for (uint32_t l = LZ_LANE(), once_ = 1; once_; once_ = 0)
-#define LZ_IF_LANE0_ONLY if (LZ_LANE() == 0)
+#define LZ_IF_LANE0_ONLY   /* every lane stores the same value to the same address: no branch needed */
 #define LZ_SYNC() __syncwarp()
 #define LZ_LANEVAR(T, name) T name
 #define LZ_LV(name, l) name
 #define LZ_DEV __device__ __forceinline__
+// Per-lane work is written WITHOUT divergent branches and WITHOUT generic-space accesses at lane-dependent
+// addresses: either one, anywhere in the kernel, makes ptxas treat every later load as possibly divergent and
+// bracket every branch of the (uniform) decoder with convergence barriers (BSSY / BSYNC / BREAK: 3.5 % of the
+// instructions plus their latency, measured).  Loops over bytes have a uniform trip count; the lane's test
+// only predicates a load / store that names its state space.
+#define LZ_STG8_IF(ptr, val, cond)   /* window (global) */                              \
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u8 [%0], %1;\n\t}" \
+                 : : "l"(ptr), "r"((uint32_t)(val)), "r"((uint32_t)(cond)) : "memory")
+#define LZ_LDG8_IF(dst, ptr, cond)                                                      \
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.u8 %0, [%1];\n\t}" \
+                 : "+r"(dst) : "l"(ptr), "r"((uint32_t)(cond)) : "memory")
+#define LZ_LDIN8_IF(dst, ptr, cond)  /* compressed input (global, read-only) */         \
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.nc.u8 %0, [%1];\n\t}" \
+                 : "+r"(dst) : "l"(ptr), "r"((uint32_t)(cond)) : "memory")
+#define LZ_STAGE8(wc, off, dst)      /* copy stage (shared) */                          \
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(dst) : "r"((wc).s_stage + (off)) : "memory")
 #else
+#define LZ_STG8_IF(ptr, val, cond) do { if (cond) *(uint8_t *)(ptr) = (uint8_t)(val); } while (0)
+#define LZ_LDG8_IF(dst, ptr, cond) do { if (cond) (dst) = *(const uint8_t *)(ptr); } while (0)
+#define LZ_LDIN8_IF(dst, ptr, cond) do { if (cond) (dst) = *(const uint8_t *)(ptr); } while (0)
+#define LZ_STAGE8(wc, off, dst) ((dst) = (wc).stage[off])
 #define LZ_FOR_LANES(l) for (uint32_t l = 0; l < 32; l++)
 #define LZ_IF_LANE0_ONLY
 #define LZ_SYNC() ((void)0)
@@ -44,6 +64,7 @@ struct WarpCopy {
     uint32_t pend_dist;    // staged: match distance (period of an overlapping copy)
     uint8_t *stage;        // shared staging buffer of the warp: 2 x 64 bytes (V_STAGE uses the first, V_CHAIN alternates)
     uint32_t stage_sel;    // V_CHAIN: which half the NEXT copy stages into (0 / 64)
+    uint32_t s_stage;      // shared-window address of `stage` (device)
     uint8_t *out_limit;    // end of the unit's output range (staging over-reads <= 3 bytes)
     LZ_LANEVAR(uint32_t, pend_val);   // the byte, in a 32-bit register
 };
@@ -62,11 +83,14 @@ LZ_DEV void wc_commit(WarpCopy &wc) {
             LZ_CP_WAIT();
             LZ_SYNC();   // each lane reads bytes other lanes' cp.async fetched
             LZ_FOR_LANES(l) {
-                if (l < wc.pend_len) wc.pend_dst[l] = wc.stage[wc.pend_off + src_index(l, wc.pend_dist)];
+                const uint32_t live = l < wc.pend_len;
+                uint32_t v;
+                LZ_STAGE8(wc, wc.pend_off + (live ? src_index(l, wc.pend_dist) : 0u), v);
+                LZ_STG8_IF(wc.pend_dst + l, v, live);
             }
         } else {
             LZ_FOR_LANES(l) {
-                if (l < wc.pend_len) wc.pend_dst[l] = (uint8_t)LZ_LV(wc.pend_val, l);
+                LZ_STG8_IF(wc.pend_dst + l, LZ_LV(wc.pend_val, l), l < wc.pend_len);
             }
         }
         wc.pend_len = 0;
@@ -75,9 +99,22 @@ LZ_DEV void wc_commit(WarpCopy &wc) {
 }
 
 LZ_DEV void probs_fill(uint16_t *p, uint32_t n) {  // initProbs, prob.go:3-7
-    LZ_FOR_LANES(l) {
-        for (uint32_t i = l; i < n; i += 32) p[i] = (uint16_t)kProbInit;
+#if defined(__CUDA_ARCH__)
+    // uniform trip count, predicated store that names its state space (tables live in shared memory, or in
+    // the HBM workspace when lc+lp > 4)
+    if (__isShared(p)) {
+        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(p) + 2u * LZ_LANE();
+        for (uint32_t b = 0; b < n; b += 32)
+            asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %1, %2;\n\t@q st.shared.u16 [%0], %3;\n\t}"
+                         : : "r"(sa + 2u * b), "r"(b + LZ_LANE()), "r"(n), "r"(kProbInit) : "memory");
+    } else {
+        for (uint32_t b = 0; b < n; b += 32)
+            asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %1, %2;\n\t@q st.global.u16 [%0], %3;\n\t}"
+                         : : "l"(p + b + LZ_LANE()), "r"(b + LZ_LANE()), "r"(n), "r"(kProbInit) : "memory");
     }
+#else
+    for (uint32_t i = 0; i < n; i++) p[i] = (uint16_t)kProbInit;
+#endif
 }
 
 // state.Reset (state.go:79-121): every table back to 1024, rep0..3 = 0, state = 0.
@@ -119,11 +156,15 @@ LZ_DEV bool f2_enter(Dec &d, const uint8_t *gpos, uint8_t *inbuf) {
     const uint64_t span = (uint64_t)(d.in_end - g0);
     const uint32_t avail = span >= kF2Stage ? kF2Stage : ((uint32_t)span & ~15u);   // whole 16-byte chunks of this unit only
     const uint32_t l = LZ_LANE();
-    if (16u * l + 16u <= avail) {
-        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(g0) + l);
-        reinterpret_cast<uint4 *>(inbuf)[l] = w;
+    {   // predicated, not branched (avail >= 112: lanes beyond it re-load chunk 0 and do not store)
+        const bool live = 16u * l + 16u <= avail;
+        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(g0) + (live ? l : 0u));
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n\t}"
+                     : : "r"(d.sIn + 16u * l), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w), "r"((uint32_t)live) : "memory");
+        const uint8_t *pf = g0 + kF2Stage + 128u * (l & 3u);
+        if (pf >= d.in_end) pf = g0;                 // (same prefetch from every lane group: harmless)
+        LZ_PREFETCH_L2(pf);
     }
-    if (l < 4 && g0 + kF2Stage + 128u * l < d.in_end) LZ_PREFETCH_L2(g0 + kF2Stage + 128u * l);
     __syncwarp();
     if (d.ctx_pending == 1) {   // context bytes held as values (careful decoder's convention): fold them in
         d.prev_byte = d.ctx_a;
@@ -150,7 +191,7 @@ LZ_DEV void publish_progress(Dec &d, const WarpCopy &wc) {
         if (blocks != d.pub) {
             __threadfence_system();      // every lane: its window stores are visible before the counter is
             __syncwarp();
-            if (LZ_LANE() == 0) *(volatile uint32_t *)d.prog = blocks;
+            *(volatile uint32_t *)d.prog = blocks;   // every lane, same value
             d.pub = blocks;
         }
     }
@@ -231,7 +272,7 @@ LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8
                 const uint8_t *a0 = src - off;
                 const uint32_t nch = (off + need + 3) >> 2;      // <= 9
                 LZ_FOR_LANES(l) {
-                    if (l < nch) LZ_CP_ASYNC4(wc.stage + 4 * l, a0 + 4 * l);
+                    if (l < nch) LZ_CP_ASYNC4(wc.stage + 4 * l, a0 + 4 * l);   // (V_STAGE experiments only)
                 }
                 LZ_CP_COMMIT();
                 wc.pend_len = len;
@@ -246,8 +287,13 @@ LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8
                 // This decoder does its common copies itself (lzgpu_fast2.cuh); what arrives here is rare
                 // (longer than 32 bytes, self-overlapping, or at the head / tail of a unit): copied at once,
                 // the context of a following literal read back from the window.
-                LZ_FOR_LANES(l) {
-                    for (uint32_t i = l; i < len; i += 32) dst[i] = src[far ? i : src_index(i, dist)];
+                for (uint32_t b = 0; b < len; b += 32) {
+                    LZ_FOR_LANES(l) {
+                        const uint32_t i = b + l, live = i < len;
+                        uint32_t v = 0;
+                        LZ_LDG8_IF(v, src + (live ? (far ? i : src_index(i, dist)) : 0u), live);
+                        LZ_STG8_IF(dst + i, v, live);
+                    }
                 }
                 LZ_SYNC();
                 d.prev_byte = dst[len - 1];
@@ -257,14 +303,20 @@ LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8
                 if (len <= 32) {
                     // deferred in registers: load now, store at the next commit
                     LZ_FOR_LANES(l) {
-                        if (l < len) LZ_LV(wc.pend_val, l) = src[far ? l : src_index(l, dist)];
+                        const uint32_t live = l < len;
+                        LZ_LDG8_IF(LZ_LV(wc.pend_val, l), src + (live ? (far ? l : src_index(l, dist)) : 0u), live);
                     }
                     wc.pend_len = len;
                     wc.pend_dst = dst;
                     wc.pend_staged = 0;
                 } else {
-                    LZ_FOR_LANES(l) {
-                        for (uint32_t i = l; i < len; i += 32) dst[i] = src[far ? i : src_index(i, dist)];
+                    for (uint32_t b = 0; b < len; b += 32) {
+                        LZ_FOR_LANES(l) {
+                            const uint32_t i = b + l, live = i < len;
+                            uint32_t v = 0;
+                            LZ_LDG8_IF(v, src + (live ? (far ? i : src_index(i, dist)) : 0u), live);
+                            LZ_STG8_IF(dst + i, v, live);
+                        }
                     }
                 }
                 // context for a literal that may follow: the last byte of the match and the byte at
@@ -325,6 +377,7 @@ LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     wc.out_limit = io.out + io.out_cap;
     set_props(d, u.lc, u.lp, u.pb);
     set_shared_addrs(d, P, io.inbuf, io.stage);
+    wc.s_stage = d.sStage;
     d.prog = io.progress;
     d.out0 = io.out;
     d.pub = 0;
@@ -375,6 +428,7 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     wc.out_limit = io.out + io.out_cap;
     set_props(d, u.lc, u.lp, u.pb);
     set_shared_addrs(d, P, io.inbuf, io.stage);
+    wc.s_stage = d.sStage;
     d.prog = io.progress;
     d.out0 = io.out;
     d.pub = 0;
@@ -460,8 +514,14 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
             if (!short_payload) n = usz;
             if ((uint64_t)(out_limit - d.outp) < n) { status = LZGPU_OUTPUT_OVERFLOW; consumed = (uint64_t)(payload - io.in); break; }
             uint8_t *dst = d.outp;
-            LZ_FOR_LANES(l) {
-                for (uint64_t i = l; i < n; i += 32) dst[i] = LZ_LD_IN8(payload + i);
+            for (uint64_t b = 0; b < n; b += 32) {
+                LZ_FOR_LANES(l) {
+                    const uint64_t i = b + l;
+                    const uint32_t live = i < n;
+                    uint32_t v = 0;
+                    LZ_LDIN8_IF(v, payload + (live ? i : 0), live);
+                    LZ_STG8_IF(dst + i, v, live);
+                }
             }
             LZ_SYNC();
             d.outp = dst + n;
