@@ -377,7 +377,7 @@ def main():
             line["e2e"] = {"value": g_out / e2e_t_max / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(g_comp),
                            "d2h_bytes_per_step": int(g_out), "ms_per_step": e2e_t_max * 1e3,
                            "rank0_breakdown_ms": {"h2d": e2e["h2d_ms"], "kernel": e2e["kernel_ms"], "d2h": e2e["d2h_ms"]},
-                           "api": "lzgpu_decode_batch (pinned host buffers)"}
+                           "api": "lzgpu_decode_batch (pinned host buffers; the units read the compressed input from host memory over PCIe while they decode, finished 64 KiB output blocks are copied out while the kernel runs)"}
         if world == 1 and not args.no_cpu_baseline:
             idx = cpu_sample(distinct, cores, args.streams)
             cpu_pass(blob, offs, lens, idx[:max(1, len(idx) // 4)], args.size, cores)  # warm

@@ -280,6 +280,7 @@ struct DevState {
     // streamed D2H: second stream, host-mapped progress counters (grow-only)
     cudaStream_t copy_stream = nullptr;
     uint32_t *h_progress = nullptr, *d_progress = nullptr;
+    uint64_t *h_tails = nullptr, *d_tails = nullptr;   // host-mapped (source offset, destination offset, length) per unit
     uint64_t progress_cap = 0;
 };
 
@@ -345,6 +346,7 @@ extern "C" void lzgpu_ctx_destroy(lzgpu_ctx *c) {
         if (d.stream) cudaStreamDestroy(d.stream);
         if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
         if (d.h_progress) cudaFreeHost(d.h_progress);
+        if (d.h_tails) cudaFreeHost(d.h_tails);
         if (d.d_in) cudaFree(d.d_in);
         if (d.d_out) cudaFree(d.d_out);
     }
@@ -590,8 +592,37 @@ int ensure(uint8_t *&ptr, uint64_t &cap, uint64_t need) {
     return 0;
 }
 
-void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base, uint8_t *out_base,
-               lzgpu_result *results) {
+// Pinned (device-accessible) host memory under unified addressing: the device pointer of [p, p + len), else null.
+const uint8_t *device_view_of_host(const uint8_t *p, uint64_t len) {
+    if (!p || !len) return nullptr;
+    cudaPointerAttributes a, b;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess || cudaPointerGetAttributes(&b, p + len - 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a.type != cudaMemoryTypeHost || b.type != cudaMemoryTypeHost || !a.devicePointer || !b.devicePointer) return nullptr;
+    if ((const uint8_t *)b.devicePointer - (const uint8_t *)a.devicePointer != (ptrdiff_t)(len - 1)) return nullptr;
+    return (const uint8_t *)a.devicePointer;
+}
+
+__global__ void lzgpu_tail_copy_kernel(const uint64_t *desc, const uint8_t *src_base, uint8_t *dst_base) {
+    // desc[3k..3k+2] = source offset, destination offset, length of unit k's tail; grid = (units, parts)
+    const uint64_t so = desc[3 * blockIdx.x], dof = desc[3 * blockIdx.x + 1], len = desc[3 * blockIdx.x + 2];
+    const uint8_t *s = src_base + so;
+    uint8_t *d = dst_base + dof;
+    const uint64_t tid = (uint64_t)blockIdx.y * blockDim.x + threadIdx.x, nth = (uint64_t)gridDim.y * blockDim.x;
+    if ((((uintptr_t)s ^ (uintptr_t)d) & 15) == 0) {
+        const uint64_t head = min(len, (uint64_t)((16 - ((uintptr_t)s & 15)) & 15));
+        const uint64_t nv = (len - head) >> 4;
+        for (uint64_t i = tid; i < head; i += nth) d[i] = s[i];
+        const uint4 *sv = reinterpret_cast<const uint4 *>(s + head);
+        uint4 *dv = reinterpret_cast<uint4 *>(d + head);
+        for (uint64_t i = tid; i < nv; i += nth) dv[i] = sv[i];
+        for (uint64_t i = head + (nv << 4) + tid; i < len; i += nth) d[i] = s[i];
+    } else {
+        for (uint64_t i = tid; i < len; i += nth) d[i] = s[i];
+    }
+}
+
+void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base, uint64_t in_size, uint8_t *out_base,
+               uint64_t out_size, lzgpu_result *results) {
     DevState &ds = ctx->devs[dev_index];
     auto cuda_fail = [&](cudaError_t e, const char *what) {
         sh.rc = e == cudaErrorMemoryAllocation ? LZGPU_E_NOMEM : LZGPU_E_CUDA;
@@ -609,16 +640,22 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
     }
     std::vector<uint64_t> ioff, ooff, host_out_off(n);
     for (size_t k = 0; k < n; k++) host_out_off[k] = sh.units[k].out_off;
-    layout_ranges(ir, ioff, sh.in_runs, sh.in_bytes);
+    // Compressed input in pinned host memory is read by the units straight over PCIe (each byte is read
+    // once, 512 bytes at a time, at ~1/400 of the link's rate): no H2D copy ahead of the kernel.  Pageable
+    // input is packed into a device slab first.  (LZGPU_NO_ZEROCOPY_IN=1 forces the slab.)
+    const uint8_t *zc_in = getenv("LZGPU_NO_ZEROCOPY_IN") ? nullptr : device_view_of_host(in_base, in_size);
+    uint8_t *zc_out = getenv("LZGPU_NO_TAIL_KERNEL") ? nullptr : const_cast<uint8_t *>(device_view_of_host(out_base, out_size));
+    if (zc_in) sh.in_bytes = in_size;
+    else layout_ranges(ir, ioff, sh.in_runs, sh.in_bytes);
     layout_ranges(orr, ooff, sh.out_runs, sh.out_bytes);
-    for (size_t k = 0; k < n; k++) { sh.units[k].in_off = ioff[k]; sh.units[k].out_off = ooff[k]; }
-    if (ensure(ds.d_in, ds.in_cap, sh.in_bytes + 16) || ensure(ds.d_out, ds.out_cap, sh.out_bytes + 16)) {
+    for (size_t k = 0; k < n; k++) { if (!zc_in) sh.units[k].in_off = ioff[k]; sh.units[k].out_off = ooff[k]; }
+    if ((!zc_in && ensure(ds.d_in, ds.in_cap, sh.in_bytes + 16)) || ensure(ds.d_out, ds.out_cap, sh.out_bytes + 16)) {
         sh.rc = LZGPU_E_NOMEM;
         sh.err = "cudaMalloc of the shard's input/output slabs failed";
         return;
     }
     lzgpu_plan *plan = nullptr;
-    int rc = lzgpu_plan_create(ctx, dev_index, sh.units.data(), (int64_t)n, sh.in_bytes + 16, sh.out_bytes + 16, &plan);
+    int rc = lzgpu_plan_create(ctx, dev_index, sh.units.data(), (int64_t)n, zc_in ? in_size : sh.in_bytes + 16, sh.out_bytes + 16, &plan);
     if (rc != LZGPU_E_OK) { sh.rc = rc; sh.err = g_last_error; return; }
     // Streamed D2H for large shards: the kernel publishes, per unit, how many 64 KiB blocks of its output
     // are final (host-mapped counters); this thread polls them while the kernel runs and sends finished
@@ -630,13 +667,17 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
         if (!ds.copy_stream && cudaStreamCreateWithFlags(&ds.copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); stream_out = false; }
         if (stream_out && ds.progress_cap < n) {
             if (ds.h_progress) cudaFreeHost(ds.h_progress);
-            ds.h_progress = nullptr; ds.d_progress = nullptr; ds.progress_cap = 0;
+            if (ds.h_tails) cudaFreeHost(ds.h_tails);
+            ds.h_progress = nullptr; ds.d_progress = nullptr; ds.h_tails = nullptr; ds.d_tails = nullptr; ds.progress_cap = 0;
             const size_t want = n + (n >> 2) + 64;
             if (cudaHostAlloc(&ds.h_progress, want * sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess ||
-                cudaHostGetDevicePointer(&ds.d_progress, ds.h_progress, 0) != cudaSuccess) {
+                cudaHostGetDevicePointer(&ds.d_progress, ds.h_progress, 0) != cudaSuccess ||
+                cudaHostAlloc(&ds.h_tails, want * 3 * sizeof(uint64_t), cudaHostAllocMapped) != cudaSuccess ||
+                cudaHostGetDevicePointer(&ds.d_tails, ds.h_tails, 0) != cudaSuccess) {
                 cudaGetLastError();
                 if (ds.h_progress) cudaFreeHost(ds.h_progress);
-                ds.h_progress = nullptr; ds.d_progress = nullptr;
+                if (ds.h_tails) cudaFreeHost(ds.h_tails);
+                ds.h_progress = nullptr; ds.d_progress = nullptr; ds.h_tails = nullptr; ds.d_tails = nullptr;
                 stream_out = false;
             } else {
                 ds.progress_cap = want;
@@ -656,7 +697,7 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
     }
     cudaEventRecord(e1, ds.stream);
     if (sh.rc == 0) {
-        rc = lzgpu_plan_launch(plan, ds.d_in, ds.d_out, ds.stream);
+        rc = lzgpu_plan_launch(plan, zc_in ? zc_in : ds.d_in, ds.d_out, ds.stream);
         if (rc != LZGPU_E_OK) { sh.rc = rc; sh.err = g_last_error; }
     }
     cudaEventRecord(e2, ds.stream);
@@ -682,6 +723,19 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
             }
             if (sh.rc != 0) break;
         }
+        if (zc_out && sh.rc == 0) {
+            // the tails, by ONE kernel that writes the caller's (pinned) buffer over PCIe: a thousand small
+            // cudaMemcpyAsync calls cost more host time than the bytes take to move
+            for (size_t k = 0; k < n; k++) {
+                const uint64_t cap = sh.units[k].out_cap, from = std::min<uint64_t>(copied[k] * kBlock, cap);
+                ds.h_tails[3 * k] = sh.units[k].out_off + from;
+                ds.h_tails[3 * k + 1] = host_out_off[k] + from;
+                ds.h_tails[3 * k + 2] = cap - from;
+            }
+            lzgpu_tail_copy_kernel<<<dim3((unsigned)n, 2), 256, 0, ds.copy_stream>>>(ds.d_tails, ds.d_out, zc_out);
+            const cudaError_t ce = cudaGetLastError();
+            if (ce != cudaSuccess) cuda_fail(ce, "tail copy kernel");
+        } else
         for (size_t k = 0; k < n && sh.rc == 0; k++)           // the tails
             send(k, std::min<uint64_t>(copied[k] * kBlock, sh.units[k].out_cap), sh.units[k].out_cap);
         cudaEventRecord(e3, ds.copy_stream);
@@ -752,11 +806,11 @@ extern "C" int lzgpu_decode_batch(lzgpu_ctx *ctx, const lzgpu_unit *units, int64
         s.units.push_back(u);
     }
     if (nd == 1) {
-        run_shard(ctx, 0, shards[0], in_base, out_base, results);
+        run_shard(ctx, 0, shards[0], in_base, in_size, out_base, out_size, results);
     } else {
         std::vector<std::thread> th;
         for (int d = 0; d < nd; d++)
-            th.emplace_back([&, d]() { run_shard(ctx, d, shards[(size_t)d], in_base, out_base, results); });
+            th.emplace_back([&, d]() { run_shard(ctx, d, shards[(size_t)d], in_base, in_size, out_base, out_size, results); });
         for (auto &t : th) t.join();
     }
     lzgpu_stats st;

@@ -106,6 +106,41 @@ def test_full_size_batch_properties(ctx):
         assert g.status == L.OK and len(g.data) == 1 << 20 and zlib.crc32(g.data) == crcs[i]
 
 
+@pytest.mark.parametrize("shift", [0, 3])
+def test_pinned_host_buffers(ctx, shift, monkeypatch):
+    """Pinned caller buffers take the zero-copy route (units read the compressed input straight from host
+    memory, unit tails written back by one kernel); pageable buffers and LZGPU_NO_ZEROCOPY_IN=1 /
+    LZGPU_NO_TAIL_KERNEL=1 take the slab route.  Same bytes, same results, whatever the alignment."""
+    import torch
+    distinct = 6
+    plains = [K.text_block(2000 + i, (1 << 20) - 37 * i) for i in range(distinct)]
+    streams = [K.compress_alone(p) for p in plains]
+    bad = bytearray(streams[0]); bad[len(bad) // 2] ^= 0x55
+    n = 70
+    pick = [i % distinct for i in range(n)]
+    ss = [streams[i] for i in pick] + [bytes(bad), streams[1][:5000]]
+    units, in_np, out_size, _ = B.build_alone_batch(ss, [1 << 20] * len(ss))
+    pin_in = torch.empty(in_np.size + 64, dtype=torch.uint8).pin_memory()
+    pin_out = torch.empty(out_size + 64, dtype=torch.uint8).pin_memory()
+    a_in = pin_in.numpy()[shift:shift + in_np.size]
+    a_in[:] = in_np
+    a_out = pin_out.numpy()[shift:shift + out_size]
+    a_out[:] = 0xEE
+    res, st = ctx.decode_batch(units, a_in, a_out)
+    monkeypatch.setenv("LZGPU_NO_ZEROCOPY_IN", "1")
+    monkeypatch.setenv("LZGPU_NO_TAIL_KERNEL", "1")
+    b_out = np.full(out_size, 0xEE, dtype=np.uint8)
+    res2, st2 = ctx.decode_batch(units, in_np, b_out)
+    assert st.h2d_ms < st2.h2d_ms or st2.h2d_ms == 0
+    for k, (r, r2, u) in enumerate(zip(res, res2, units)):
+        assert (r.status, r.err_site, r.bytes_out, r.bytes_in, r.final_code) == (r2.status, r2.err_site, r2.bytes_out, r2.bytes_in, r2.final_code), k
+        assert a_out[u.out_off:u.out_off + r.bytes_out].tobytes() == b_out[u.out_off:u.out_off + r.bytes_out].tobytes(), k
+        if k < n:
+            assert r.status == L.OK and a_out[u.out_off:u.out_off + r.bytes_out].tobytes() == plains[pick[k]], k
+    assert res[n].status != L.OK or a_out[units[n].out_off:units[n].out_off + res[n].bytes_out].tobytes() != plains[0]
+    assert res[n + 1].status == L.OK_INPUT_EXHAUSTED
+
+
 def test_large_literal_tables_in_hbm(ctx):
     """lc+lp > 4 needs literal tables beyond shared memory (the reference accepts any prop < 225,
     reader1.go:210-221).  liblzma cannot write such streams, so build one by re-labelling: a stream
