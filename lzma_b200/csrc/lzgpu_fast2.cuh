@@ -36,21 +36,43 @@ namespace lzgpu {
 //   %4 the block's result, %5.. its inputs.
 #define F2_REGS                                                                         \
     ".reg .pred one, nz, q0, q1, mbp, ne;\n\t"                                          \
-    ".reg .b32 t, bd, k, pn, p, pz, lo, hi, ya, yb, yc, nS;\n\t"
+    ".reg .b32 t, tn, u3, bd, k, pn, p, pz, lo, hi, ya, yb, yc, nS;\n\t"
+
+// range >> 11 of the NEXT step is selected from the two shifts of the un-normalised range (>> 3 if the
+// normalisation will shift it left by 8, else >> 11) as soon as that range exists, instead of being taken
+// from the normalised range: the serial chain  bound -> bit -> range -> normalise? -> shift -> >> 11 -> bound
+// loses one link for one more instruction (ptxas folds the select into a predicated shift).  tn carries it
+// from step to step inside one asm block; F2_T0 starts a block.  Measured: lone warp -2.2 %, bench shape -0.8 %.
+#ifndef F2_TN
+#define F2_TN 1
+#endif
+#if F2_TN
+#define F2_T0 "shr.u32 tn, %0, 11;\n\t"
+#define F2_TLOAD ""
+#define F2_TAHEAD "shr.u32 u3, %0, 3;\n\tshr.u32 tn, %0, 11;\n\t"
+#define F2_TSEL "@nz mov.b32 tn, u3;\n\t"
+#else
+#define F2_T0 ""
+#define F2_TLOAD "shr.u32 tn, %0, 11;\n\t"
+#define F2_TAHEAD ""
+#define F2_TSEL ""
+#endif
 
 // DecodeBit (range_decoder.go:57-98) on probability register P, predicate Q = the bit, followed by the
 // normalisation: consume the byte in hand, fetch the one after it.  Ordered along the critical path.
 // (The input address is advanced BEFORE the load: an add placed after it would have to wait until the
 // load has read its address register -- ~10 cycles in every step, measured.)
 #define F2_CORE(P, Q)                                                                   \
-    "shr.u32 t, %0, 11;\n\t"                                                            \
-    "mul.lo.u32 bd, t, " P ";\n\t"                                                      \
+    F2_TLOAD                                                                            \
+    "mul.lo.u32 bd, tn, " P ";\n\t"                                                     \
     "sub.s32 k, 31, " P ";\n\t"                                                         \
     "setp.ge.u32 " Q ", %1, bd;\n\t"                                                    \
     "sub.u32 t, %0, bd;\n\t"                                                            \
     "selp.b32 %0, t, bd, " Q ";\n\t"                                                    \
     "setp.lt.u32 nz, %0, 0x1000000;\n\t"                                                \
+    F2_TAHEAD                                                                           \
     "@" Q " sub.u32 %1, %1, bd;\n\t"                                                    \
+    F2_TSEL                                                                             \
     "@nz shl.b32 %0, %0, 8;\n\t"                                                        \
     "@nz add.u32 %3, %3, 1;\n\t"                                                        \
     "@nz mad.lo.u32 %1, %1, 256, %2;\n\t"                                               \
@@ -70,15 +92,17 @@ namespace lzgpu {
 // Instruction ORDER follows the critical path (range -> bound -> bit -> range -> normalised range): ptxas
 // breaks scheduling ties by source order.
 #define F2_STEP_BODY(YC, YN, QC, NS, LOADS, P, PN, STORE)                               \
-    "shr.u32 t, %0, 11;\n\t"                                                            \
-    "mul.lo.u32 bd, t, " P ";\n\t"                                                      \
+    F2_TLOAD                                                                            \
+    "mul.lo.u32 bd, tn, " P ";\n\t"                                                     \
     "mad.lo.u32 " YN ", " YC ", 2, " NS ";\n\t"                                         \
     "sub.s32 k, 31, " P ";\n\t"                                                         \
     "setp.ge.u32 " QC ", %1, bd;\n\t"                                                   \
     "sub.u32 t, %0, bd;\n\t"                                                            \
     "selp.b32 %0, t, bd, " QC ";\n\t"                                                   \
-    "selp.b32 " PN ", hi, lo, " QC ";\n\t"                                              \
     "setp.lt.u32 nz, %0, 0x1000000;\n\t"                                                \
+    F2_TAHEAD                                                                           \
+    "selp.b32 " PN ", hi, lo, " QC ";\n\t"                                              \
+    F2_TSEL                                                                             \
     "@" QC " sub.u32 %1, %1, bd;\n\t"                                                   \
     "@" QC " add.u32 " YN ", " YN ", 4;\n\t"                                            \
     "@nz shl.b32 %0, %0, 8;\n\t"                                                        \
@@ -131,7 +155,7 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
 // one adaptive bit whose probability PV was loaded from shared address A earlier
 #define F2_BIT(d, PV, A, BIT)                                                           \
     asm volatile("{\n\t" F2_REGS                                                        \
-                 F2_CORE("%6", "one") F2_UPD("%6", "one")                               \
+                 F2_T0 F2_CORE("%6", "one") F2_UPD("%6", "one")                         \
                  "st.shared.u16 [%5], pn;\n\t"                                          \
                  "selp.u32 %4, 1, 0, one;\n\t"                                          \
                  F2_NORM "}"                                                            \
@@ -139,7 +163,7 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
 
 // 6-level tree at byte address BASE (posSlot, decompress.go:441-486): result = node index 64..127
 #define F2_TREE6(d, OUT, BASE)                                                          \
-    asm volatile("{\n\t" F2_REGS F2_ROOT("%5")                                          \
+    asm volatile("{\n\t" F2_REGS F2_ROOT("%5") F2_T0                                    \
                  F2_L0("%5", F2_LD) F2_L1(F2_LD) F2_L2(F2_LD) F2_L3(F2_LD) F2_L4(F2_LD) F2_L5(F2_NOLD) \
                  "add.u32 t, yb, nS;\n\tshr.u32 %4, t, 2;\n\t}"                          \
                  : F2_IO(d), "=&r"(OUT) : "r"(BASE) : "memory")
@@ -147,7 +171,7 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
 // The root and its children (P0, PLO, PHI) were loaded by the caller before the direct bits.
 #define F2_TREE4(d, OUT, BASE, P0, PLO, PHI)                                            \
     asm volatile("{\n\t" F2_REGS                                                        \
-                 "neg.s32 nS, %5;\n\tmov.b32 p, %6;\n\tmov.b32 lo, %7;\n\tmov.b32 hi, %8;\n\tadd.u32 yb, %5, 4;\n\t" \
+                 "neg.s32 nS, %5;\n\tmov.b32 p, %6;\n\tmov.b32 lo, %7;\n\tmov.b32 hi, %8;\n\tadd.u32 yb, %5, 4;\n\t" F2_T0 \
                  F2_L0("%5", F2_LD) F2_L1(F2_LD) F2_L2(F2_LD) F2_L3(F2_NOLD)            \
                  "add.u32 t, yc, nS;\n\tshr.u32 %4, t, 2;\n\t}"                          \
                  : F2_IO(d), "=&r"(OUT) : "r"(BASE), "r"(P0), "r"(PLO), "r"(PHI) : "memory")
@@ -198,13 +222,13 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
     L "END:\n\t"
 #define F2_LEN(d, OUT, SLEN, SLOW)                                                      \
     asm volatile("{\n\t" F2_REGS ".reg .b32 bs, pc2, pr0;\n\t"                          \
-                 F2_LEN_LOADS F2_LEN_BODY("F2_LEN_") "}"                                \
+                 F2_LEN_LOADS F2_T0 F2_LEN_BODY("F2_LEN_") "}"                                \
                  : F2_IO(d), "=&r"(OUT) : "r"(SLEN), "r"(SLOW) : "memory")
 // isRep (decompress.go:195-213; cell at AREP, value PREP loaded earlier) and, when it decodes 0, the
 // match length: the length coder's cells are in flight while isRep decodes.  OUT = 0xFFFFFFFF for a rep.
 #define F2_ISREP_LEN(d, OUT, SLEN, SLOW, AREP, PREP)                                    \
     asm volatile("{\n\t" F2_REGS ".reg .b32 bs, pc2, pr0;\n\t"                          \
-                 F2_LEN_LOADS                                                           \
+                 F2_LEN_LOADS F2_T0                                                     \
                  F2_CORE("%8", "one") F2_UPD("%8", "one")                               \
                  "st.shared.u16 [%7], pn;\n\t"                                          \
                  "mov.u32 %4, 0xffffffff;\n\t"                                          \
@@ -241,7 +265,7 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
 
 #define F2_LIT(d, OUT, S, MB, MATCHED)                                                  \
     asm volatile("{\n\t" F2_REGS ".reg .b32 xa, xb, ua, ub, pa, pb, v, pmis;\n\t"       \
-                 "neg.s32 nS, %5;\n\t"                                                  \
+                 "neg.s32 nS, %5;\n\t" F2_T0                                            \
                  "setp.ne.u32 one, %7, 0;\n\t"                                          \
                  "@one bra.uni F2_LIT_M;\n\t"                                           \
                  "ld.shared.u16 p, [%5+2];\n\t"                                         \
