@@ -215,10 +215,19 @@ def main():
         raise SystemExit("bench.py: no CUDA device; lzma_b200 has no CPU decode path")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL prints its version banner to STDOUT when NCCL_DEBUG asks for it; stdout carries the one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("LZGPU_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner to STDOUT (at NCCL_DEBUG=VERSION / WARN / INFO); stdout carries the one
+        # JSON line, so the communicator is created (and used once) with fd 1 pointing at stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if world > 1:

@@ -260,3 +260,18 @@ def test_batch_over_all_visible_gpus():
             assert g.status == L.OK and g.data == p
             devs.add(g.device)
         assert len(devs) == c.n_devices or c.n_devices > len(plains)
+        # the same over pinned caller buffers (every GPU reads its shard's input from host memory) and with
+        # enough output per GPU (>= 32 MiB) for the streamed D2H + tail kernel
+        import torch
+        big = [K.text_block(950 + i, 1 << 20) for i in range(4)]
+        streams = [K.compress_alone(b, preset=1) for b in big]
+        n = 36 * c.n_devices
+        units, in_np, out_size, _ = B.build_alone_batch([streams[i % 4] for i in range(n)], [1 << 20] * n)
+        h_in = torch.empty(in_np.size, dtype=torch.uint8).pin_memory()
+        h_out = torch.empty(out_size, dtype=torch.uint8).pin_memory()
+        h_in.numpy()[:] = in_np
+        res, st = c.decode_batch(units, h_in.numpy(), h_out.numpy())
+        out = h_out.numpy()
+        assert st.devices == c.n_devices
+        for k, (r, u) in enumerate(zip(res, units)):
+            assert r.status == L.OK and out[u.out_off:u.out_off + r.bytes_out].tobytes() == big[k % 4], k
