@@ -183,6 +183,11 @@ int lzgpu_plan_create(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *units, in
 int lzgpu_plan_launch(lzgpu_plan *plan, const uint8_t *d_in, uint8_t *d_out, void *stream);
 int lzgpu_plan_results(lzgpu_plan *plan, lzgpu_result *results, lzgpu_stats *stats);
 int lzgpu_plan_launch_count(const lzgpu_plan *plan); /* kernels one plan_launch enqueues */
+/* On-device verification (no reference analogue): CRC-32 (zlib's crc32, the .xz
+ * CHECK_CRC32 polynomial) of every unit's decoded bytes out[out_off, out_off + bytes_out), computed on the
+ * GPU after plan_launch on the same stream and returned in crc[n_units] (host memory).  Units that did not
+ * run, or produced nothing, give 0.  Lets a batch too large to copy back be checked where it lies. */
+int lzgpu_plan_crc32(lzgpu_plan *plan, const uint8_t *d_out, uint32_t *crc);
 void lzgpu_plan_destroy(lzgpu_plan *plan);
 
 #ifdef __cplusplus

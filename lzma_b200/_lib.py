@@ -65,6 +65,7 @@ SYMBOLS = [
     ("lzgpu_plan_launch", C.c_int, [_vp, _u8p, _u8p, _vp]),
     ("lzgpu_plan_results", C.c_int, [_vp, C.POINTER(Result), C.POINTER(Stats)]),
     ("lzgpu_plan_launch_count", C.c_int, [_vp]),
+    ("lzgpu_plan_crc32", C.c_int, [_vp, _u8p, C.POINTER(C.c_uint32)]),
     ("lzgpu_plan_destroy", None, [_vp]),
 ]
 

@@ -142,6 +142,12 @@ class Plan:
         L.check(L.lib().lzgpu_plan_results(self._h, res, C.byref(st)))
         return res, st
 
+    def crc32(self, d_out_ptr: int) -> np.ndarray:
+        """CRC-32 (zlib's) of every unit's decoded bytes, computed on the device (lzgpu_plan_crc32)."""
+        crc = (C.c_uint32 * max(self.n, 1))()
+        L.check(L.lib().lzgpu_plan_crc32(self._h, d_out_ptr, crc))
+        return np.frombuffer(crc, dtype=np.uint32)[:self.n].copy()
+
     def close(self):
         if self._h:
             L.lib().lzgpu_plan_destroy(self._h)

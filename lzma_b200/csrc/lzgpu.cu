@@ -502,6 +502,109 @@ extern "C" int lzgpu_plan_launch(lzgpu_plan *p, const uint8_t *d_in, uint8_t *d_
     return LZGPU_E_OK;
 }
 
+// ------------------------------------------------------------------ on-device verification
+// CRC-32 (IEEE 802.3, reflected 0xEDB88320: zlib's crc32, the .xz CHECK_CRC32) of every unit's decoded bytes,
+// so that a batch too large to copy back (BASELINE config 5: 64 GiB) is verified where it lies.
+// One CTA per unit.  The unit's bytes are cut into 256 slices of equal length L, RIGHT-aligned (the leading
+// slices may be short or empty); each thread runs slicing-by-4 over its slice, then the 256 partial CRCs are
+// folded in a tree with  crc(A || B) = crc(A) * x^(8|B|) mod P  xor  crc(B)  (every right operand is full,
+// so step k multiplies by the one power x^(8 L 2^k)).
+namespace {
+constexpr uint32_t kCrcPoly = 0xEDB88320u;
+__host__ __device__ inline uint32_t crc_mulmod(uint32_t a, uint32_t b) {   // a * b mod P, reflected bit order
+    uint32_t m = 1u << 31, p = 0;
+    for (;;) {
+        if (a & m) { p ^= b; if ((a & (m - 1)) == 0) break; }
+        m >>= 1;
+        b = (b & 1) ? (b >> 1) ^ kCrcPoly : b >> 1;
+    }
+    return p;
+}
+__host__ __device__ inline uint32_t crc_x_pow_8n(uint64_t n) {             // x^(8n) mod P
+    uint32_t sq = crc_mulmod(1u << 30, 1u << 30);   // x^2
+    sq = crc_mulmod(sq, sq);                        // x^4
+    sq = crc_mulmod(sq, sq);                        // x^8
+    uint32_t p = 1u << 31;                          // x^0
+    while (n) {
+        if (n & 1) p = crc_mulmod(sq, p);
+        sq = crc_mulmod(sq, sq);
+        n >>= 1;
+    }
+    return p;
+}
+
+__global__ void __launch_bounds__(256) lzgpu_crc32_kernel(const lzgpu_unit *units, const lzgpu_result *results,
+                                                          const uint8_t *out_base, uint32_t *crc, int64_t n) {
+    __shared__ uint32_t T[4][256];
+    __shared__ uint32_t part[256];
+    __shared__ uint32_t powk[8];
+    const uint32_t t = threadIdx.x;
+    {   // slicing tables: T[0] the byte table, T[j][b] = T[j-1][b] advanced by one zero byte
+        uint32_t c = t;
+        for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ kCrcPoly : c >> 1;
+        T[0][t] = c;
+        __syncthreads();
+        for (int j = 1; j < 4; j++) { c = (c >> 8) ^ T[0][c & 0xFF]; T[j][t] = c; }
+        __syncthreads();   // every warp reads every entry
+    }
+    for (int64_t ui = blockIdx.x; ui < n; ui += gridDim.x) {
+        const uint64_t total = results[ui].status == LZGPU_NOT_RUN ? 0 : results[ui].bytes_out;
+        const uint8_t *base = out_base + units[ui].out_off;
+        const uint64_t L = ((total + 255) / 256 + 3) & ~(uint64_t)3;
+        if (t == 0) {
+            uint32_t pw = crc_x_pow_8n(L);
+            for (int k = 0; k < 8; k++) { powk[k] = pw; pw = crc_mulmod(pw, pw); }
+        }
+        // slice t = [total - (256 - t) L, total - (255 - t) L) clipped at 0
+        const uint64_t back_hi = (uint64_t)(256 - t) * L, back_lo = (uint64_t)(255 - t) * L;
+        const uint64_t lo = back_hi >= total ? 0 : total - back_hi, hi = back_lo >= total ? 0 : total - back_lo;
+        uint32_t c = 0;
+        if (hi > lo) {
+            const uint8_t *p = base + lo, *e = base + hi;
+            c = 0xFFFFFFFFu;
+            while (p < e && ((uintptr_t)p & 15)) c = (c >> 8) ^ T[0][(c ^ *p++) & 0xFF];
+            for (; p + 16 <= e; p += 16) {
+                const uint4 w = *reinterpret_cast<const uint4 *>(p);
+                const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    c ^= ws[q];
+                    c = T[3][c & 0xFF] ^ T[2][(c >> 8) & 0xFF] ^ T[1][(c >> 16) & 0xFF] ^ T[0][c >> 24];
+                }
+            }
+            while (p < e) c = (c >> 8) ^ T[0][(c ^ *p++) & 0xFF];
+            c = ~c;
+        }
+        part[t] = c;
+        __syncthreads();
+        for (int k = 0; k < 8; k++) {
+            const uint32_t step = 1u << k;
+            if ((t & (2 * step - 1)) == 0) part[t] = crc_mulmod(powk[k], part[t]) ^ part[t + step];
+            __syncthreads();
+        }
+        if (t == 0) crc[ui] = part[0];
+        __syncthreads();
+    }
+}
+}  // namespace
+
+extern "C" int lzgpu_plan_crc32(lzgpu_plan *p, const uint8_t *d_out, uint32_t *crc) {
+    if (!p || !p->launched || (p->n > 0 && (!d_out || !crc))) return fail(LZGPU_E_INVALID, "plan_crc32: plan was not launched / null argument");
+    if (p->n == 0) return LZGPU_E_OK;
+    DevState &ds = p->ctx->devs[p->dev_index];
+    CUDA_TRY(cudaSetDevice(ds.device));
+    uint32_t *d_crc = nullptr;
+    CUDA_TRY(cudaMalloc(&d_crc, sizeof(uint32_t) * (size_t)p->n));
+    const unsigned grid = (unsigned)std::min<int64_t>(p->n, 148 * 16);
+    lzgpu_crc32_kernel<<<grid, 256, 0, p->last_stream>>>(p->d_units, p->d_results, d_out, d_crc, p->n);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(crc, d_crc, sizeof(uint32_t) * (size_t)p->n, cudaMemcpyDeviceToHost, p->last_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->last_stream);
+    cudaFree(d_crc);
+    if (e != cudaSuccess) return fail(LZGPU_E_CUDA, std::string("plan_crc32: ") + cudaGetErrorString(e));
+    return LZGPU_E_OK;
+}
+
 extern "C" int lzgpu_plan_results(lzgpu_plan *p, lzgpu_result *results, lzgpu_stats *stats) {
     if (!p || !p->launched) return fail(LZGPU_E_INVALID, "plan_results: plan was not launched");
     DevState &ds = p->ctx->devs[p->dev_index];

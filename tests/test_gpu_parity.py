@@ -92,6 +92,59 @@ def test_device_resident_plan(ctx):
     plan.close()
 
 
+def test_device_crc32_of_units(ctx):
+    """lzgpu_plan_crc32 (on-device verification) == zlib.crc32 of each unit's decoded bytes: ragged sizes around
+    the slicing and alignment boundaries, an empty unit, a failed unit (CRC of the bytes decoded before the
+    error), unaligned output offsets."""
+    import torch
+    sizes = [0, 1, 3, 4, 5, 15, 16, 17, 255, 256, 257, 1023, 4096, 4097, 65_537, 300_001, 1 << 20]
+    plains = [K.text_block(700 + i, n) if n else b"" for i, n in enumerate(sizes)]
+    streams = [K.compress_alone(p) for p in plains]
+    bad = bytearray(streams[-2]); bad[len(bad) // 2] ^= 0x10
+    streams.append(bytes(bad)); plains.append(None)
+    units, in_buf, out_size, _ = B.build_alone_batch(streams, [max(len(p), 1) if p is not None else 300_001 for p in plains])
+    off = 0
+    for k, u in enumerate(units):          # odd output offsets: the CRC kernel must not assume alignment
+        u.out_off = off + (k % 7)
+        off = _ru16(u.out_off + u.out_cap)
+    out_size = off + 16
+    d_in = torch.from_numpy(in_buf).cuda()
+    d_out = torch.zeros(out_size, dtype=torch.uint8, device="cuda")
+    plan = ctx.plan(units, in_buf.nbytes, out_size)
+    plan.launch(d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream or 1)
+    crc = plan.crc32(d_out.data_ptr())
+    res, _ = plan.results()
+    out = d_out.cpu().numpy()
+    for k, p in enumerate(plains):
+        got = out[units[k].out_off:units[k].out_off + res[k].bytes_out].tobytes()
+        if p is not None:
+            assert res[k].status == L.OK and got == p, k
+        assert int(crc[k]) == zlib.crc32(got), (k, len(got))
+    plan.close()
+    # many units at once (more than the CRC kernel's grid, every CTA busy from its first cycle): 5 distinct
+    # streams, each unit decoding into its own range
+    distinct, n_units, size = 5, 5000, 48_000
+    plains = [K.text_block(800 + i, size) for i in range(distinct)]
+    t_units, in_buf, _, _ = B.build_alone_batch([K.compress_alone(p) for p in plains], [size] * distinct)
+    units = (L.Unit * n_units)()
+    for k in range(n_units):
+        C.memmove(C.byref(units[k]), C.byref(t_units[k % distinct]), C.sizeof(L.Unit))
+        units[k].out_off, units[k].out_cap = k * size, size
+    d_in = torch.from_numpy(in_buf).cuda()
+    d_out = torch.zeros(n_units * size + 16, dtype=torch.uint8, device="cuda")
+    plan = ctx.plan(units, in_buf.nbytes, n_units * size + 16)
+    plan.launch(d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream or 1)
+    for _ in range(3):
+        crc = plan.crc32(d_out.data_ptr())
+        want = np.array([zlib.crc32(plains[k % distinct]) for k in range(n_units)], dtype=np.uint32)
+        assert np.array_equal(crc, want), np.nonzero(crc != want)[0][:8]
+    plan.close()
+
+
+def _ru16(x):
+    return (x + 15) // 16 * 16
+
+
 def test_full_size_batch_properties(ctx):
     """BASELINE-sized units (1 MiB) in a batch larger than the SM count: checksum per unit against the
     plaintext's, and the decoded size; every unit of the same stream must give the same bytes."""
