@@ -312,7 +312,13 @@ def main():
     bad = [(k, res[k].status) for k in range(n) if res[k].status != L.OK or res[k].bytes_out != args.size]
     assert not bad, f"decode failed on units {bad[:5]}"
 
-    # bit-exact check of the timed output: CRC32 of every decoded unit whose plaintext CRC is cached
+    # bit-exact check of the timed output: CRC32 of every decoded unit whose plaintext CRC is cached, computed
+    # where the bytes lie (lzgpu_plan_crc32) and again on the host
+    dev_crc = plan.crc32(d_out.data_ptr())
+    for k, j in enumerate(mine):
+        s = int(g_stream[j])
+        if s < len(crc):
+            assert int(dev_crc[k]) == int(crc[s]), f"unit {k} (stream {s}) decoded wrongly (device CRC)"
     out_host = d_out.cpu().numpy()
     checked = 0
     for k, j in enumerate(mine):
@@ -336,7 +342,10 @@ def main():
             r2, st2 = ctx.decode_batch(units, hin, hout)
         t_e2e = (time.perf_counter() - t0) / e2e_steps
         assert all(r2[k].status == L.OK for k in range(n))
-        assert zlib.crc32(hout[:args.size]) == zlib.crc32(d_out[:args.size].cpu().numpy())
+        for k, j in enumerate(mine):     # every unit of the end-to-end output, too
+            s = int(g_stream[j])
+            if s < len(crc):
+                assert zlib.crc32(hout[units[k].out_off:units[k].out_off + args.size]) == int(crc[s]), f"e2e: unit {k} decoded wrongly"
         e2e = {"t": t_e2e, "h2d": comp_bytes, "d2h": out_bytes, "kernel_ms": st2.kernel_ms, "h2d_ms": st2.h2d_ms, "d2h_ms": st2.d2h_ms}
 
     # ---- max over ranks ----
@@ -373,7 +382,7 @@ def main():
                        "compressed_bytes_total": int(g_comp), "decompressed_bytes_total": int(g_out),
                        "sharding": "LPT by compressed size over ranks, no collective",
                        "l2": "per-step working set (compressed in + decoded out) exceeds the 126 MB L2",
-                       "verified": f"CRC32 of {checked} decoded units vs plaintext; status OK + size for all"},
+                       "verified": f"CRC32 of {checked} decoded units vs plaintext, on the device (lzgpu_plan_crc32) and on the host, for the device-resident and the end-to-end output; status OK + size for all"},
             "clocks": clocks,
             "gpu_launches": args.steps * plan.launch_count,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -1,0 +1,498 @@
+// lzma_reader.cpp -- the reader API of kulaginds/lzma in C++ over liblzgpu.so (see include/lzma_reader.hpp).
+// Host glue only: header parsing, input slurping, LZMA2 wave cutting, status -> error mapping.  Every decoded
+// byte comes from lzgpu_decode_batch; there is no CPU decode path here either.
+#include "lzma_reader.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+namespace lzma {
+
+// ---------------------------------------------------------------- errors / io
+namespace errors {
+error New(const std::string &msg) { return std::make_shared<const ErrorValue>(ErrorValue{msg, nullptr}); }
+error Errorf(const std::string &prefix, const error &err) {
+    return std::make_shared<const ErrorValue>(ErrorValue{prefix + ": " + (err ? err->msg : "<nil>"), err});
+}
+bool Is(const error &err, const error &target) {
+    for (const ErrorValue *e = err.get(); e; e = e->wrapped.get())
+        if (e == target.get()) return true;
+    return false;
+}
+}  // namespace errors
+
+namespace io {
+const error EOF_ = errors::New("EOF");
+const error ErrUnexpectedEOF = errors::New("unexpected EOF");
+
+std::pair<int64_t, error> Copy(Writer &dst, Reader &src) {
+    std::vector<uint8_t> buf(32 * 1024);
+    int64_t written = 0;
+    for (;;) {
+        auto [n, rerr] = src.Read(buf.data(), buf.size());
+        if (n > 0) {
+            auto [w, werr] = dst.Write(buf.data(), (size_t)n);
+            written += w;
+            if (werr) return {written, werr};
+        }
+        if (rerr) return {written, errors::Is(rerr, EOF_) ? nullptr : rerr};
+    }
+}
+
+std::pair<int, error> BytesReader::Read(uint8_t *p, size_t len) {
+    if (pos_ >= n_) return {0, len ? EOF_ : nullptr};
+    const size_t n = std::min(len, n_ - pos_);
+    memcpy(p, d_ + pos_, n);
+    pos_ += n;
+    return {(int)n, nullptr};
+}
+std::pair<uint8_t, error> BytesReader::ReadByte() {
+    if (pos_ >= n_) return {0, EOF_};
+    return {d_[pos_++], nullptr};
+}
+}  // namespace io
+
+const error ErrCorrupted = errors::New("corrupted");
+const error ErrIncorrectProperties = errors::New("incorrect LZMA properties");
+const error ErrResultError = errors::New("result error");
+const error ErrDictOutOfRange = errors::New("dictionary capacity is out of range");
+const error ErrUnexpectedLZMA2Code = errors::New("unexpected lzma2 code");
+const error ErrNoLZMAReader = errors::New("no lzma reader on chunkLZMAResetState");
+const error errNeedOneReader = errors::New("lzma: need exactly one reader");
+const error errInsufficientProperties = errors::New("lzma2: not enough properties");
+const error errAlreadyClosed = errors::New("lzma: already closed");
+const error ErrOutputOverflow = errors::New("lzgpu: output capacity too small");
+
+namespace {
+// bufio.NewReader(r) as far as the readers need it: a ByteReader over a Reader
+class bufReader : public io::ByteReader, public io::Reader {
+  public:
+    explicit bufReader(io::Reader *r) : r_(r), buf_(64 * 1024) {}
+    std::pair<uint8_t, error> ReadByte() override {
+        if (lo_ == hi_) {
+            if (err_) return {0, err_};
+            auto [n, e] = r_->Read(buf_.data(), buf_.size());
+            lo_ = 0;
+            hi_ = n > 0 ? (size_t)n : 0;
+            if (e) err_ = e;
+            else if (n == 0) err_ = io::EOF_;
+            if (lo_ == hi_) return {0, err_};
+        }
+        return {buf_[lo_++], nullptr};
+    }
+    std::pair<int, error> Read(uint8_t *p, size_t len) override {
+        if (lo_ < hi_) {
+            const size_t n = std::min(len, hi_ - lo_);
+            memcpy(p, buf_.data() + lo_, n);
+            lo_ += n;
+            return {(int)n, nullptr};
+        }
+        if (err_) return {0, err_};
+        return r_->Read(p, len);
+    }
+  private:
+    io::Reader *r_;
+    std::vector<uint8_t> buf_;
+    size_t lo_ = 0, hi_ = 0;
+    error err_;
+};
+
+// everything the stream still holds, appended to `to`
+void slurp(io::ByteReader *br, std::vector<uint8_t> &to) {
+    if (auto *r = dynamic_cast<io::Reader *>(br)) {
+        std::vector<uint8_t> chunk(1 << 20);
+        for (;;) {
+            auto [n, e] = r->Read(chunk.data(), chunk.size());
+            if (n > 0) to.insert(to.end(), chunk.begin(), chunk.begin() + n);
+            if (e || n == 0) return;
+        }
+    }
+    for (;;) {
+        auto [b, e] = br->ReadByte();
+        if (e) return;
+        to.push_back(b);
+    }
+}
+
+size_t read_exact(io::Reader *r, uint8_t *p, size_t n) {
+    size_t got = 0;
+    while (got < n) {
+        auto [k, e] = r->Read(p + got, n - got);
+        if (k > 0) got += (size_t)k;
+        if (e || k == 0) break;
+    }
+    return got;
+}
+}  // namespace
+
+// ---------------------------------------------------------------- engine
+std::pair<std::shared_ptr<Engine>, error> Engine::New(const std::vector<int> &devices) {
+    std::shared_ptr<Engine> e(new Engine());
+    const int rc = lzgpu_ctx_create(devices.empty() ? nullptr : devices.data(), (int)devices.size(), &e->ctx_);
+    if (rc != LZGPU_E_OK) return {nullptr, errors::New(std::string("lzgpu: ") + lzgpu_last_error())};
+    return {e, nullptr};
+}
+std::pair<std::shared_ptr<Engine>, error> Engine::Default() {
+    static std::mutex mu;
+    static std::shared_ptr<Engine> def;
+    std::lock_guard<std::mutex> lock(mu);
+    if (def) return {def, nullptr};
+    auto [e, err] = New();
+    if (!err) def = e;
+    return {e, err};
+}
+Engine::~Engine() {
+    if (ctx_) lzgpu_ctx_destroy(ctx_);
+}
+int Engine::Devices() const { return lzgpu_ctx_device_count(ctx_); }
+
+std::pair<std::vector<Result>, error> Engine::DecodeBatch(const std::vector<Unit> &units, const uint8_t *in, size_t in_len,
+                                                          uint8_t *out, size_t out_len) {
+    std::vector<Result> res(units.size());
+    static const uint8_t nothing[16] = {0};
+    const int rc = lzgpu_decode_batch(ctx_, units.data(), (int64_t)units.size(), in ? in : nothing, in_len, out, out_len,
+                                      res.data(), nullptr);
+    if (rc != LZGPU_E_OK) return {{}, errors::New(std::string("lzgpu: ") + lzgpu_last_error())};
+    return {std::move(res), nullptr};
+}
+
+error Engine::StatusError(int status) {
+    switch (status) {
+    case LZGPU_OK:
+    case LZGPU_OK_INPUT_EXHAUSTED: return nullptr;   // truncated input is a clean EOF in the reference (reader1.go:246-249)
+    case LZGPU_RESULT_ERROR: return ErrResultError;
+    case LZGPU_INCORRECT_PROPERTIES: return ErrIncorrectProperties;
+    case LZGPU_UNEXPECTED_EOF: return io::ErrUnexpectedEOF;
+    case LZGPU_OUTPUT_OVERFLOW: return ErrOutputOverflow;
+    default: return errors::New("lzgpu: unexpected status " + std::to_string(status));
+    }
+}
+
+// ---------------------------------------------------------------- reader1.go
+std::tuple<uint8_t, uint8_t, uint8_t, error> DecodeProp(uint8_t d) {   // reader1.go:210-221
+    uint8_t lc, pb, lp;
+    if (lzgpu_decode_prop(d, &lc, &pb, &lp) != LZGPU_OK) return {0, 0, 0, ErrIncorrectProperties};
+    return {lc, pb, lp, nullptr};
+}
+std::pair<uint32_t, error> DecodeDictSize(const uint8_t properties[4]) { return {lzgpu_decode_dict_size(properties), nullptr}; }
+uint64_t DecodeUnpackSize(const uint8_t header[8]) { return lzgpu_decode_unpack_size(header); }
+uint32_t DecodeDictSize2(uint8_t encodedDictSize) { return lzgpu_decode_dict_size2(encodedDictSize); }
+
+error Reader1::initialize() {   // rangeDecoder.Init: 5 bytes, the first must be 0 (range_decoder.go:27-46)
+    payload_.clear();
+    for (int i = 0; i < 5; i++) {
+        auto [b, e] = in_->ReadByte();
+        if (e) {
+            if (!payload_.empty() && payload_[0] != 0) return errors::Errorf("rangeDec.Init", ErrResultError);
+            return errors::Errorf("rangeDec.Init", e);
+        }
+        payload_.push_back(b);
+    }
+    if (payload_[0] != 0) return errors::Errorf("rangeDec.Init", ErrResultError);
+    return nullptr;
+}
+
+void Reader1::decode() {
+    decoded_ = true;
+    slurp(in_, payload_);
+    if (!eng_) {
+        auto [e, err] = Engine::Default();
+        if (err) { err_ = err; return; }
+        eng_ = e;
+    }
+    Unit u;
+    memset(&u, 0, sizeof u);
+    u.kind = LZGPU_KIND_LZMA1_RAW;
+    u.lc = lc_; u.lp = lp_; u.pb = pb_;
+    u.dict_size = dict_;
+    u.unpack_size = unpack_;
+    u.in_off = 0;
+    u.in_len = payload_.size();
+    const bool known = unpack_ != ~0ull;
+    uint64_t cap = std::max<uint64_t>(1 << 16, 8 * (uint64_t)payload_.size());
+    if (known) cap = std::min<uint64_t>(cap, std::max<uint64_t>(unpack_, 1));
+    for (;;) {
+        u.out_off = 0;
+        u.out_cap = cap;
+        out_.resize((size_t)std::max<uint64_t>(cap, 16));
+        auto [res, err] = eng_->DecodeBatch({u}, payload_.data(), payload_.size(), out_.data(), out_.size());
+        if (err) { out_.clear(); err_ = err; return; }
+        const bool can_grow = known ? cap < unpack_ : cap < (1ull << 40);
+        if (res[0].status == LZGPU_OUTPUT_OVERFLOW && can_grow) {   // the streaming reader has no capacity: grow, decode again
+            cap = known ? std::min<uint64_t>(cap * 8, unpack_) : cap * 8;
+            continue;
+        }
+        out_.resize((size_t)res[0].bytes_out);
+        err_ = Engine::StatusError(res[0].status);
+        break;
+    }
+    payload_.clear();
+    payload_.shrink_to_fit();
+}
+
+std::pair<int, error> Reader1::Read(uint8_t *p, size_t len) {   // reader1.go:223-254
+    if (!decoded_) decode();
+    const size_t n = std::min(len, out_.size() - pos_);
+    if (n) {
+        memcpy(p, out_.data() + pos_, n);
+        pos_ += n;
+    }
+    if (n == len && n > 0) return {(int)n, nullptr};
+    isEndOfStream = true;
+    if (err_) {
+        error e = err_;
+        err_ = nullptr;
+        return {(int)n, e};
+    }
+    return {(int)n, io::EOF_};
+}
+
+void Reader1::Reset() { isEndOfStream = false; }
+
+error Reader1::Reopen(io::ByteReader &inStream, uint64_t unpackSize) {   // reader1.go:166-176
+    isEndOfStream = false;
+    in_ = &inStream;
+    owned_in_.reset();
+    unpack_ = unpackSize;
+    out_.clear();
+    pos_ = 0;
+    decoded_ = false;
+    err_ = nullptr;
+    return initialize();
+}
+
+std::pair<std::unique_ptr<Reader1>, error> NewReader1(io::ByteReader &inStream, std::shared_ptr<Engine> eng) {
+    // reader1.go:18-24 + initializeFull (:77-101): header and range-coder preamble read eagerly
+    std::unique_ptr<Reader1> r(new Reader1());
+    r->in_ = &inStream;
+    r->eng_ = std::move(eng);
+    uint8_t h[13];
+    for (int i = 0; i < 13; i++) {
+        auto [b, e] = inStream.ReadByte();
+        if (e) {
+            if (i == 0) return {std::move(r), e};
+            return {std::move(r), errors::Errorf(i < 5 ? "decode dict size" : "decode unpack size", e)};
+        }
+        h[i] = b;
+        if (i == 0) {
+            auto [lc, pb, lp, perr] = DecodeProp(b);
+            if (perr) return {std::move(r), errors::Errorf("decode prop", perr)};
+            r->lc_ = lc; r->pb_ = pb; r->lp_ = lp;
+        }
+    }
+    r->dict_ = DecodeDictSize(h + 1).first;
+    r->unpack_ = DecodeUnpackSize(h + 5);
+    error e = r->initialize();
+    return {std::move(r), e};
+}
+
+std::pair<std::unique_ptr<io::ReadCloser>, error> NewLZMADecompressorForSevenZip(
+    const std::vector<uint8_t> &props, uint64_t unpackSize, const std::vector<io::ReadCloser *> &readers,
+    std::shared_ptr<Engine> eng) {   // reader1.go:32-61
+    if (readers.size() != 1) return {nullptr, errNeedOneReader};
+    if (props.size() < 5) return {nullptr, ErrIncorrectProperties};
+    auto [lc, pb, lp, perr] = DecodeProp(props[0]);
+    if (perr) return {nullptr, perr};
+    auto [dictSize, derr] = DecodeDictSize(props.data() + 1);
+    if (derr) return {nullptr, derr};
+    std::unique_ptr<Reader1> r(new Reader1());
+    if (auto *br = dynamic_cast<io::ByteReader *>(readers[0])) r->in_ = br;
+    else {
+        r->owned_in_.reset(new bufReader(readers[0]));
+        r->in_ = r->owned_in_.get();
+    }
+    r->eng_ = std::move(eng);
+    r->lc_ = lc; r->lp_ = lp; r->pb_ = pb;
+    r->dict_ = dictSize;
+    r->unpack_ = unpackSize;
+    error e = r->initialize();
+    return {std::unique_ptr<io::ReadCloser>(new readCloser(readers[0], std::move(r))), e};
+}
+
+// ---------------------------------------------------------------- reader2.go
+error Reader2::initialize() {
+    if (dict_ < (1u << 12)) dict_ = 8u << 20;   // reader2.go:88-91
+    uint8_t c;
+    if (read_exact(in_, &c, 1) < 1) return io::ErrUnexpectedEOF;   // reader2.go:103-110
+    buf_.assign(1, c);
+    if (c == 0 || (c >= 3 && c < 0x80)) return nullptr;
+    const size_t hl = c < 0x80 ? 3 : (c < 0xC0 ? 5 : 6);
+    uint8_t rest[6];
+    const size_t got = read_exact(in_, rest, hl - 1);
+    buf_.insert(buf_.end(), rest, rest + got);
+    if (got < hl - 1) return io::ErrUnexpectedEOF;   // reader2.go:121-128
+    if (c >= 0x80) {
+        // first LZMA chunk: NewReader1ForReader2 -> DecodeProp + rangeDec.Init (reader2.go:146-153)
+        const uint8_t prop = hl == 6 ? buf_[5] : 0;
+        if (prop >= 225) return ErrIncorrectProperties;
+        uint8_t pre;
+        if (read_exact(in_, &pre, 1) < 1) return errors::Errorf("rangeDec.Init", io::EOF_);
+        buf_.push_back(pre);
+        if (pre != 0) return errors::Errorf("rangeDec.Init", ErrResultError);
+    }
+    return nullptr;
+}
+
+bool Reader2::fill(size_t need) {   // at least `need` unread bytes in buf_ (false: the input ended first)
+    while (buf_.size() - rd_ < need && !in_eof_) {
+        const size_t want = std::max<size_t>(1 << 20, need - (buf_.size() - rd_));
+        const size_t old = buf_.size();
+        buf_.resize(old + want);
+        auto [n, e] = in_->Read(buf_.data() + old, want);
+        buf_.resize(old + (n > 0 ? (size_t)n : 0));
+        if (e || n <= 0) in_eof_ = true;
+    }
+    return buf_.size() - rd_ >= need;
+}
+
+// Uncompressed chunk with dictionary reset at `pos`: does the first LZMA chunk after it (if one comes before the
+// next reset) reset the state and carry properties?  Otherwise it inherits the previous unit's coder
+// (reader2.go:155-165) and must stay in the same wave.
+bool Reader2::independentFrom(size_t pos) {
+    const size_t p0 = pos;
+    for (;;) {
+        rd_ = p0;
+        if (!fill(pos - p0 + 3)) return true;
+        const uint8_t c = buf_[pos];
+        if (c == 0 || (c >= 3 && c < 0x80) || c >= 0xE0 || (c == 1 && pos != p0)) return true;
+        if (c >= 0x80) return c >= 0xC0;
+        pos += 3 + (((size_t)buf_[pos + 1] << 8) | buf_[pos + 2]) + 1;
+    }
+}
+
+// Walk chunk headers (reader2.go:100-214) from rd_ until wave_bytes of output are covered and the next chunk starts
+// a unit that inherits nothing.  Returns true when this wave is the stream's last.
+bool Reader2::nextWave(std::vector<uint8_t> &wave) {
+    const size_t start = rd_;
+    size_t pos = rd_, out = 0;
+    bool first = true;
+    for (;;) {
+        rd_ = pos;
+        if (!fill(1)) { wave.assign(buf_.begin() + start, buf_.end()); rd_ = buf_.size(); return true; }   // ran off the input: the scanner reports it
+        const uint8_t ctrl = buf_[pos];
+        if (ctrl == 0 || (ctrl >= 3 && ctrl < 0x80)) {   // end of stream (0x03-0x7F too, reader2.go:185-198)
+            rd_ = pos + 1;
+            wave.assign(buf_.begin() + start, buf_.begin() + pos + 1);
+            return true;
+        }
+        const bool enough = !first && out >= wave_bytes;
+        const bool reset = ctrl >= 0xE0 || (ctrl == 1 && enough && independentFrom(pos));
+        rd_ = pos;
+        if (reset && enough) {   // the wave ends before this chunk; terminate it
+            wave.assign(buf_.begin() + start, buf_.begin() + pos);
+            wave.push_back(0);
+            return false;
+        }
+        const size_t hl = ctrl < 0x80 ? 3 : (ctrl < 0xC0 ? 5 : 6);
+        if (!fill(hl)) { wave.assign(buf_.begin() + start, buf_.end()); rd_ = buf_.size(); return true; }
+        size_t usz = (((size_t)buf_[pos + 1] << 8) | buf_[pos + 2]) + 1, payload;
+        if (ctrl >= 0x80) {
+            usz += (size_t)(ctrl & 0x1F) << 16;
+            payload = (((size_t)buf_[pos + 3] << 8) | buf_[pos + 4]) + 1;
+        } else payload = usz;
+        if (!fill(hl + payload)) { wave.assign(buf_.begin() + start, buf_.end()); rd_ = buf_.size(); return true; }
+        pos += hl + payload;
+        out += usz;
+        first = false;
+    }
+}
+
+void Reader2::decodeWave() {
+    decoded_ = true;
+    std::vector<uint8_t> wave;
+    const bool last = nextWave(wave);
+    if (rd_ > (8u << 20)) {   // drop what has been handed to the GPU
+        buf_.erase(buf_.begin(), buf_.begin() + rd_);
+        rd_ = 0;
+    }
+    out_.clear();
+    pos_ = 0;
+    if (!eng_) {
+        auto [e, err] = Engine::Default();
+        if (err) { err_ = err; last_ = true; return; }
+        eng_ = e;
+    }
+    std::vector<Unit> units(64);
+    uint64_t total = 0;
+    int32_t sst = 0;
+    int64_t n = lzgpu_scan_lzma2(wave.data(), wave.size(), dict_, units.data(), (int64_t)units.size(), &total, &sst);
+    if (n > (int64_t)units.size()) {
+        units.resize((size_t)n);
+        n = lzgpu_scan_lzma2(wave.data(), wave.size(), dict_, units.data(), (int64_t)units.size(), &total, &sst);
+    }
+    if (n < 0) { err_ = errors::New(std::string("lzgpu: ") + lzgpu_last_error()); last_ = true; return; }
+    units.resize((size_t)n);
+    out_.resize((size_t)std::max<uint64_t>(total, 16));
+    auto [res, err] = eng_->DecodeBatch(units, wave.data(), wave.size(), out_.data(), out_.size());
+    if (err) { out_.clear(); err_ = err; last_ = true; return; }
+    // the bytes of the units before the first failing one are delivered with the failure, as the reference's
+    // reader would have delivered them
+    uint64_t n_out = 0;
+    int status = sst == LZGPU_OK || n > 0 ? LZGPU_OK : sst;
+    for (size_t k = 0; k < units.size(); k++) {
+        n_out = units[k].out_off + res[k].bytes_out;
+        if (res[k].status != LZGPU_OK) { status = res[k].status; break; }
+    }
+    out_.resize((size_t)n_out);
+    err_ = Engine::StatusError(status);
+    last_ = last || err_ != nullptr;
+}
+
+std::pair<int, error> Reader2::Read(uint8_t *p, size_t len) {   // reader2.go:216-250
+    if (!decoded_) decodeWave();
+    while (pos_ == out_.size() && !last_ && len) decodeWave();   // previous wave delivered: the next one
+    const size_t n = std::min(len, out_.size() - pos_);
+    if (n) {
+        memcpy(p, out_.data() + pos_, n);
+        pos_ += n;
+    }
+    if (n == len && n > 0) return {(int)n, nullptr};
+    if (!last_) return {(int)n, nullptr};
+    if (err_) {
+        error e = err_;
+        err_ = nullptr;
+        return {(int)n, e};
+    }
+    return {(int)n, io::EOF_};
+}
+
+std::pair<std::unique_ptr<Reader2>, error> NewReader2(io::Reader &inStream, int dictSize, std::shared_ptr<Engine> eng) {
+    std::unique_ptr<Reader2> r(new Reader2());   // reader2.go:26-41
+    r->in_ = &inStream;
+    r->dict_ = (uint32_t)dictSize;
+    r->eng_ = std::move(eng);
+    error e = r->initialize();
+    return {std::move(r), e};
+}
+
+std::pair<std::unique_ptr<io::ReadCloser>, error> NewLZMA2DecompressorForSevenZip(
+    const std::vector<uint8_t> &props, uint64_t, const std::vector<io::ReadCloser *> &readers,
+    std::shared_ptr<Engine> eng) {   // reader2.go:49-75
+    if (readers.size() != 1) return {nullptr, errNeedOneReader};
+    if (props.size() != 1) return {nullptr, errInsufficientProperties};
+    std::unique_ptr<Reader2> r(new Reader2());
+    r->in_ = readers[0];
+    r->dict_ = DecodeDictSize2(props[0]);
+    r->eng_ = std::move(eng);
+    error e = r->initialize();
+    return {std::unique_ptr<io::ReadCloser>(new readCloser(readers[0], std::move(r))), e};
+}
+
+// ---------------------------------------------------------------- readcloser.go
+error readCloser::Close() {
+    if (!c_ || !r_) return errAlreadyClosed;   // readcloser.go:17-19
+    if (error e = c_->Close()) return errors::Errorf("lzma: error closing", e);
+    c_ = nullptr;
+    r_.reset();
+    return nullptr;
+}
+
+std::pair<int, error> readCloser::Read(uint8_t *p, size_t len) {
+    if (!r_) return {0, errAlreadyClosed};
+    auto [n, err] = r_->Read(p, len);
+    if (err && !errors::Is(err, io::EOF_)) err = errors::Errorf("lzma: error reading", err);   // readcloser.go:36-38
+    return {n, err};
+}
+
+}  // namespace lzma
