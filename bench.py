@@ -136,9 +136,9 @@ def cpu_pass(blob, offs, lens, sample_idx, size, threads):
 
 
 def cpu_sample(distinct: int, cores: int, streams: int = 1024):
-    """Bounded sample of the workload for the CPU legs: ~1 s of wall time on all cores
-    (about 35 ms of one core per 1 MiB stream -> 10-30 core-seconds)."""
-    n = max(32, min(streams, cores * 32))
+    """Bounded sample of the workload for the CPU legs: 1-2 s of wall time on all cores (about 17 ms of one
+    core per 1 MiB stream: the whole 1 024-stream workload is ~17 core-seconds; fewer streams on small hosts)."""
+    n = max(32, min(streams, cores * 64))
     return np.arange(n) % distinct
 
 
