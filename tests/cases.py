@@ -142,3 +142,50 @@ def encoder_cases(seed: int = 3, heavy: bool = True):
         cases.append((f"enc_flip_lc8lp4_{r}", bytes(b), len(d) + 50_000))
         cases.append((f"enc_trunc_lc8lp4_{r}", s[:rng.randrange(14, len(s))], len(d) + 50_000))
     return cases
+
+
+def fuzz_cases(n: int = 1200, seed: int = 7):
+    """Hostile variants of valid .lzma streams long enough for the fast decoder to be running when the damage
+    is met: single / multiple bit flips, byte overwrites, inserted and deleted bytes, truncations, wrong sizes,
+    wrong dictionary sizes, swapped property bytes.  List of (name, stream, out_cap)."""
+    rng = random.Random(seed)
+    bases = []
+    for i, (lc, lp, pb, ds, kind, size) in enumerate([
+            (3, 0, 2, 1 << 20, "text", 160_000), (0, 2, 0, 1 << 16, "mixed", 120_000), (4, 0, 4, 4096, "text", 90_000),
+            (1, 3, 1, 1 << 18, "mixed", 200_000), (3, 0, 2, 1 << 16, "random", 20_000), (2, 1, 3, 8192, "runs", 150_000)]):
+        if kind == "text":
+            d = K.text_block(300 + i, size)
+        elif kind == "mixed":
+            d = K.mixed_block(300 + i, size)
+        elif kind == "random":
+            d = K.random_block(300 + i, size)
+        else:
+            d = (b"".join(bytes([j]) * (50 + 13 * j) for j in range(60)) + b"abcd" * 9000 + K.text_block(9, 40_000))[:size]
+        mode = "eos" if i % 2 else "eos+size"
+        bases.append((K.compress_alone(d, lc, lp, pb, ds, preset=rng.choice([1, 6]), size_mode=mode), len(d)))
+    cases = []
+    for k in range(n):
+        s, size = bases[k % len(bases)]
+        b = bytearray(s)
+        op = rng.choice(["flip", "flip", "flip", "flips", "byte", "insert", "delete", "trunc", "size", "dict", "prop"])
+        if op == "flip":
+            b[rng.randrange(13, len(b))] ^= 1 << rng.randrange(8)
+        elif op == "flips":
+            for _ in range(rng.randrange(2, 6)):
+                b[rng.randrange(13, len(b))] ^= 1 << rng.randrange(8)
+        elif op == "byte":
+            b[rng.randrange(13, len(b))] = rng.randrange(256)
+        elif op == "insert":
+            b.insert(rng.randrange(18, len(b)), rng.randrange(256))
+        elif op == "delete":
+            del b[rng.randrange(18, len(b))]
+        elif op == "trunc":
+            del b[rng.randrange(13, len(b)):]
+        elif op == "size":
+            b[5:13] = struct.pack("<Q", max(0, size + rng.choice([-70_000, -300, -1, 1, 2, 300, 70_000])))
+        elif op == "dict":
+            b[1:5] = struct.pack("<I", rng.choice([0, 1, 4096, 4097, 5000, 65_535, 1 << 20]))
+        else:
+            b[0] = rng.randrange(225)
+        cases.append((f"fuzz_{k}_{op}", bytes(b), size + rng.choice([0, 1, 4096, 300_000])))
+    return cases

@@ -37,3 +37,13 @@ def test_encoder_cases(ctx):
     got = B.decode_alone_streams(ctx, [c[1] for c in cs], [c[2] for c in cs])
     for (name, s, cap), g in zip(cs, got):
         same_outcome(O.lzma_alone(s, cap), g.status, g.err_site, g.data, name)
+
+
+def test_corruption_fuzz(ctx):
+    """Hostile variants of valid streams (a third of the GPU tier's set): status, site and bytes == oracle."""
+    if ctx.variant not in (1, 33):
+        pytest.skip("fuzz on the two shipped decoders only (the others are tuning experiments)")
+    cs = cases.fuzz_cases(400)
+    got = B.decode_alone_streams(ctx, [c[1] for c in cs], [c[2] for c in cs])
+    for (name, s, cap), g in zip(cs, got):
+        same_outcome(O.lzma_alone(s, cap), g.status, g.err_site, g.data, name)

@@ -64,6 +64,31 @@ def test_lzma2_cases(ctx):
         same_outcome(O.lzma2(s, dict_size, cap + (1 << 20)), st, site, data, name, strict_site=False)
 
 
+def test_corruption_fuzz(ctx):
+    """1 200 hostile variants of valid streams in ONE batch (damage met while the fast decoder runs): status,
+    error site and delivered bytes equal the oracle's for every one, and no unit writes outside its own output
+    range (64-byte canaries between the ranges; compute-sanitizer is not available on this pool)."""
+    cs = cases.fuzz_cases()
+    units, in_buf, _, _ = B.build_alone_batch([c[1] for c in cs], [c[2] for c in cs])
+    off = 64
+    for u in units:
+        u.out_off = off
+        off = _ru16(off + u.out_cap) + 64
+    out = np.full(off, 0xA5, dtype=np.uint8)
+    res, _ = ctx.decode_batch(units, in_buf, out)
+    kinds = {}
+    prev_end = 0
+    for (name, s, cap), u, r in zip(cs, units, res):
+        want = O.lzma_alone(s, cap)
+        same_outcome(want, r.status, r.err_site, out[u.out_off:u.out_off + r.bytes_out].tobytes(), name)
+        assert r.bytes_out <= u.out_cap
+        assert (out[prev_end:u.out_off] == 0xA5).all(), f"{name}: bytes before the unit's output range were written"
+        prev_end = u.out_off + u.out_cap
+        kinds[want.status_name] = kinds.get(want.status_name, 0) + 1
+    assert (out[prev_end:] == 0xA5).all()
+    assert len(kinds) >= 4, kinds       # OK, input exhausted, result error, overflow ... all occur
+
+
 def test_unknown_size_retry(ctx):
     d = K.text_block(123, 3_000_000)     # ratio > the first capacity guess
     g = B.decode_alone_streams(ctx, [K.compress_alone(d, preset=1)])[0]
