@@ -319,6 +319,16 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
                  "F2_LIT_END:\n\t}"                                                     \
                  : F2_IO(d), "=&r"(OUT) : "r"(S), "r"(MB), "r"(MATCHED) : "memory")
 
+// plain literal whose root cell and its children (P0, PLO, PHI at S+2 / S+4 / S+6) were loaded ahead: after a
+// literal the state is < 7, so a literal that follows is a plain one whose context is the byte just decoded --
+// its cells are fetched while isMatch is still being decoded
+#define F2_LIT_PRE(d, OUT, S, P0, PLO, PHI)                                             \
+    asm volatile("{\n\t" F2_REGS                                                        \
+                 "neg.s32 nS, %5;\n\tmov.b32 p, %6;\n\tmov.b32 lo, %7;\n\tmov.b32 hi, %8;\n\tadd.u32 yb, %5, 4;\n\t" F2_T0 \
+                 F2_L0("%5", F2_LD) F2_L1(F2_LD) F2_L2(F2_LD) F2_L3(F2_LD) F2_L4(F2_LD) F2_L5(F2_LD) F2_L6(F2_LD) F2_L7(F2_NOLD) \
+                 "add.u32 t, ya, nS;\n\tshr.u32 t, t, 2;\n\tand.b32 %4, t, 255;\n\t}"  \
+                 : F2_IO(d), "=&r"(OUT) : "r"(S), "r"(P0), "r"(PLO), "r"(PHI) : "memory")
+
 // consume one input byte outside an adaptive step (direct bits, decompress.go:549-576)
 #define F2_SHIFT8(d)                                                                    \
     asm volatile("add.u32 %3, %3, 1;\n\t"                                               \
@@ -407,6 +417,7 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t 
         p_im = f2_lds16(a_im);                                                          \
         p_rep = f2_lds16(a_rep);                                                        \
     } while (0)
+    uint32_t pl_valid = 0, pl_S = 0, pl_p = 0, pl_lo = 0, pl_hi = 0;   // root cells of a literal after a literal
     for (;;) {
         if (LZ_UNLIKELY(d.ips > d.lims || d.outp > d.fast_out_end)) return OP_SWITCH;
 
@@ -414,6 +425,16 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t 
         F2_BIT(d, p_im, a_im, bit);                              // :25-42
 
         if (bit == 0) {  // literal, :44-175
+            uint32_t sym;
+            if (pl_valid) {
+                // the previous symbol was a literal too: state < 7 (plain literal), nothing pending in the window,
+                // and this literal's root cells were loaded before isMatch was decoded
+                d.state = (d.state > 3u ? d.state : 3u) - 3u;    // stateUpdateLiteral for state < 7
+                d.wpos++;
+                if (LZ_UNLIKELY(d.wpos >= d.dict_size)) { d.wpos -= d.dict_size; d.full = 1; }
+                F2_NEXT_CTX();
+                F2_LIT_PRE(d, sym, pl_S, pl_p, pl_lo, pl_hi);
+            } else {
             uint32_t prevb = d.prev_byte, matchb = d.mbyte;
             if (d.ctx_pending) {                                 // a window copy came right before: its source
                 asm volatile("cp.async.wait_group 0;" ::: "memory");   // words are (being) staged in shared memory
@@ -432,12 +453,19 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t 
             d.wpos++;
             if (LZ_UNLIKELY(d.wpos >= d.dict_size)) { d.wpos -= d.dict_size; d.full = 1; }
             F2_NEXT_CTX();
-            uint32_t sym;
             F2_LIT(d, sym, S, 0x100u | matchb, matched);
+            }
             *d.outp++ = (uint8_t)sym;                             // PutByte, :168
             d.prev_byte = sym;
+            // root cells of the literal that may follow (context: this byte, the position after it)
+            pl_S = d.sL + 0x600u * (((d.wpos & d.lp_mask) << d.lc) + (sym >> (8 - d.lc)));
+            pl_p = f2_lds16(pl_S + 2);
+            pl_lo = f2_lds16(pl_S + 4);
+            pl_hi = f2_lds16(pl_S + 6);
+            pl_valid = 1;
             continue;
         }
+        pl_valid = 0;
 
         uint32_t len;
         const uint32_t state2 = (a_im - sP - 2u * P_IS_MATCH) >> 1;   // of THIS symbol (isRep0Long, :716)

@@ -142,6 +142,10 @@ if __name__ == "__main__":
         if "--config5" in sys.argv:        # 16 384 x 4 MiB on one GPU (64 GiB of output in HBM)
             run_replicated(ctx, 16384, 4 << 20)
             sys.exit(0)
+        if "--quick-random" in sys.argv:   # incompressible data: 9 adaptive bits per byte, literals only
+            run(ctx, "random", 148, 1 << 20)
+            run(ctx, "mixed", 1024, 1 << 20)
+            sys.exit(0)
         if "--quick" in sys.argv:          # A/B of tuning variants: lone-warp latency and the bench shape
             for n in (148, 1024):
                 run(ctx, "text", n, 1 << 20)
