@@ -282,6 +282,10 @@ struct DevState {
     uint32_t *h_progress = nullptr, *d_progress = nullptr;
     uint64_t *h_tails = nullptr, *d_tails = nullptr;   // host-mapped (source offset, destination offset, length) per unit
     uint64_t progress_cap = 0;
+    // descriptors / results of the batch in flight (grow-only): the host-buffer entry point allocates nothing per
+    // call (cudaMalloc / cudaFree serialise against the other GPUs' work in a multi-GPU process: 12 ms seen)
+    uint8_t *d_desc = nullptr;
+    uint64_t desc_cap = 0;
 };
 
 struct lzgpu_ctx {
@@ -315,6 +319,7 @@ struct lzgpu_plan {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t last_stream = nullptr;
     bool launched = false;
+    bool borrowed = false;                // d_units / d_order / d_results live in the device's descriptor arena
     int variant = 0;
 };
 
@@ -347,6 +352,7 @@ extern "C" void lzgpu_ctx_destroy(lzgpu_ctx *c) {
         if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
         if (d.h_progress) cudaFreeHost(d.h_progress);
         if (d.h_tails) cudaFreeHost(d.h_tails);
+        if (d.d_desc) cudaFree(d.d_desc);
         if (d.d_in) cudaFree(d.d_in);
         if (d.d_out) cudaFree(d.d_out);
     }
@@ -358,9 +364,11 @@ extern "C" int lzgpu_ctx_device_count(const lzgpu_ctx *c) { return c ? (int)c->d
 extern "C" void lzgpu_plan_destroy(lzgpu_plan *p) {
     if (!p) return;
     cudaSetDevice(p->ctx->devs[p->dev_index].device);
-    if (p->d_units) cudaFree(p->d_units);
-    if (p->d_order) cudaFree(p->d_order);
-    if (p->d_results) cudaFree(p->d_results);
+    if (!p->borrowed) {
+        if (p->d_units) cudaFree(p->d_units);
+        if (p->d_order) cudaFree(p->d_order);
+        if (p->d_results) cudaFree(p->d_results);
+    }
     if (p->d_lit_ws) cudaFree(p->d_lit_ws);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
@@ -375,8 +383,14 @@ static size_t smem_bytes(uint32_t lit_bits, bool lit_global) {
     return sizeof(uint16_t) * probs_elems(lit_bits, lit_global) + 128 + kF2Stage;
 }
 
+static int plan_create_impl(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *units, int64_t n,
+                            uint64_t in_size, uint64_t out_size, lzgpu_plan **out, bool use_arena);
 extern "C" int lzgpu_plan_create(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *units, int64_t n,
                                  uint64_t in_size, uint64_t out_size, lzgpu_plan **out) {
+    return plan_create_impl(ctx, dev_index, units, n, in_size, out_size, out, false);
+}
+static int plan_create_impl(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *units, int64_t n,
+                            uint64_t in_size, uint64_t out_size, lzgpu_plan **out, bool use_arena) {
     if (!ctx || !out || n < 0 || (n > 0 && !units)) return fail(LZGPU_E_INVALID, "plan_create: bad arguments");
     if (dev_index < 0 || dev_index >= (int)ctx->devs.size()) return fail(LZGPU_E_INVALID, "plan_create: dev_index out of range");
     if (n > INT32_MAX) return fail(LZGPU_E_INVALID, "plan_create: too many units");
@@ -453,10 +467,27 @@ extern "C" int lzgpu_plan_create(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit
         return fail(e == cudaErrorMemoryAllocation ? LZGPU_E_NOMEM : LZGPU_E_CUDA, m);
     };
     cudaError_t e;
+    if (n > 0 && use_arena) {
+        DevState &ds = ctx->devs[dev_index];
+        const uint64_t need = (sizeof(lzgpu_unit) + sizeof(lzgpu_result) + sizeof(int32_t)) * (uint64_t)n + 512;
+        if (ds.desc_cap < need) {
+            if (ds.d_desc) cudaFree(ds.d_desc);
+            ds.d_desc = nullptr; ds.desc_cap = 0;
+            const uint64_t want = need + (need >> 2);
+            if ((e = cudaMalloc(&ds.d_desc, want)) != cudaSuccess) return bail(e, "cudaMalloc descriptor arena");
+            ds.desc_cap = want;
+        }
+        p->borrowed = true;
+        p->d_units = reinterpret_cast<lzgpu_unit *>(ds.d_desc);
+        p->d_results = reinterpret_cast<lzgpu_result *>(ds.d_desc + sizeof(lzgpu_unit) * (size_t)n);
+        p->d_order = reinterpret_cast<int32_t *>(ds.d_desc + (sizeof(lzgpu_unit) + sizeof(lzgpu_result)) * (size_t)n);
+    }
     if (n > 0) {
+        if (!use_arena) {
         if ((e = cudaMalloc(&p->d_units, sizeof(lzgpu_unit) * (size_t)n)) != cudaSuccess) return bail(e, "cudaMalloc units");
         if ((e = cudaMalloc(&p->d_results, sizeof(lzgpu_result) * (size_t)n)) != cudaSuccess) return bail(e, "cudaMalloc results");
         if ((e = cudaMalloc(&p->d_order, sizeof(int32_t) * std::max<size_t>(1, runnable.size()))) != cudaSuccess) return bail(e, "cudaMalloc order");
+        }
         if ((e = cudaMemcpy(p->d_units, p->units.data(), sizeof(lzgpu_unit) * (size_t)n, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload units");
         if (!runnable.empty() && (e = cudaMemcpy(p->d_order, runnable.data(), sizeof(int32_t) * runnable.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload order");
         if ((e = cudaMemcpy(p->d_results, p->preset.data(), sizeof(lzgpu_result) * (size_t)n, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload results");
@@ -727,6 +758,13 @@ __global__ void lzgpu_tail_copy_kernel(const uint64_t *desc, const uint8_t *src_
 void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base, uint64_t in_size, uint8_t *out_base,
                uint64_t out_size, lzgpu_result *results) {
     DevState &ds = ctx->devs[dev_index];
+    // LZGPU_TRACE=1: host-side timeline of this shard on stderr (ms since the shard started)
+    static const bool trace = getenv("LZGPU_TRACE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (trace) fprintf(stderr, "[lzgpu dev %d] %8.3f ms  %s\n", ds.device,
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(), what);
+    };
     auto cuda_fail = [&](cudaError_t e, const char *what) {
         sh.rc = e == cudaErrorMemoryAllocation ? LZGPU_E_NOMEM : LZGPU_E_CUDA;
         sh.err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -758,8 +796,9 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
         return;
     }
     lzgpu_plan *plan = nullptr;
-    int rc = lzgpu_plan_create(ctx, dev_index, sh.units.data(), (int64_t)n, zc_in ? in_size : sh.in_bytes + 16, sh.out_bytes + 16, &plan);
+    int rc = plan_create_impl(ctx, dev_index, sh.units.data(), (int64_t)n, zc_in ? in_size : sh.in_bytes + 16, sh.out_bytes + 16, &plan, true);
     if (rc != LZGPU_E_OK) { sh.rc = rc; sh.err = g_last_error; return; }
+    mark("plan created");
     // Streamed D2H for large shards: the kernel publishes, per unit, how many 64 KiB blocks of its output
     // are final (host-mapped counters); this thread polls them while the kernel runs and sends finished
     // blocks to the caller's buffer on a second stream, so that only each unit's tail is left to copy
@@ -804,6 +843,7 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
         if (rc != LZGPU_E_OK) { sh.rc = rc; sh.err = g_last_error; }
     }
     cudaEventRecord(e2, ds.stream);
+    mark("kernel enqueued");
     if (sh.rc == 0 && stream_out) {
         std::vector<uint32_t> copied(n, 0);
         volatile const uint32_t *prog = ds.h_progress;
@@ -841,6 +881,7 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
         } else
         for (size_t k = 0; k < n && sh.rc == 0; k++)           // the tails
             send(k, std::min<uint64_t>(copied[k] * kBlock, sh.units[k].out_cap), sh.units[k].out_cap);
+        mark("kernel finished, tails enqueued");
         cudaEventRecord(e3, ds.copy_stream);
         e = cudaStreamSynchronize(ds.copy_stream);
         if (e != cudaSuccess && sh.rc == 0) cuda_fail(e, "D2H (streamed) sync");
@@ -855,6 +896,7 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
     }
     e = cudaStreamSynchronize(ds.stream);
     if (e != cudaSuccess && sh.rc == 0) cuda_fail(e, "decode kernel / stream sync");
+    mark("streams idle");
     if (sh.rc == 0) {
         std::vector<lzgpu_result> tmp(n);
         lzgpu_stats st;
@@ -871,8 +913,10 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
             sh.d2h_ms = b;
         }
     }
+    mark("results read");
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
     lzgpu_plan_destroy(plan);
+    mark("plan destroyed");
 }
 
 }  // namespace
