@@ -14,7 +14,9 @@ ASSETS = os.path.join(ROOT, "tests", "golden", "ref_assets")
 
 @pytest.fixture(scope="module")
 def exe():
-    subprocess.check_call(["make", "-C", os.path.join(ROOT, "lzma_b200", "csrc"), "-s"])
+    # `reader` builds only the C++ host library and this test program (liblzgpu.so must exist: build() made it)
+    assert os.path.exists(os.path.join(ROOT, "lzma_b200", "liblzgpu.so")), "run __graft_entry__.build() first"
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "lzma_b200", "csrc"), "-s", "reader"])
     assert os.path.exists(EXE)
     return EXE
 
