@@ -61,6 +61,24 @@ func NewEngine() (*Engine, error) {
 
 func (e *Engine) Close() { C.lzgpu_ctx_destroy(e.ctx); e.ctx = nil }
 
+// PinnedBuffer is host memory the GPUs can address (lzgpu_alloc_pinned): input placed in one is read by the
+// decode kernel directly over PCIe, output written to one is streamed back while the kernel runs.
+// DecodeBatch uses pinned scratch buffers internally; callers with long-lived buffers can hold their own.
+type PinnedBuffer struct {
+	p unsafe.Pointer
+	B []byte
+}
+
+func NewPinnedBuffer(size int) (*PinnedBuffer, error) {
+	p := C.lzgpu_alloc_pinned(C.uint64_t(size))
+	if p == nil {
+		return nil, fmt.Errorf("lzgpu: %s", C.GoString(C.lzgpu_last_error()))
+	}
+	return &PinnedBuffer{p: p, B: unsafe.Slice((*byte)(p), size)}, nil
+}
+
+func (b *PinnedBuffer) Free() { C.lzgpu_free_pinned(b.p); b.p, b.B = nil, nil }
+
 // statusErr maps a per-unit status onto the package's error values (errors.go:5-12).
 func statusErr(st C.int32_t) error {
 	switch st {

@@ -183,6 +183,14 @@ int lzgpu_plan_create(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *units, in
 int lzgpu_plan_launch(lzgpu_plan *plan, const uint8_t *d_in, uint8_t *d_out, void *stream);
 int lzgpu_plan_results(lzgpu_plan *plan, lzgpu_result *results, lzgpu_stats *stats);
 int lzgpu_plan_launch_count(const lzgpu_plan *plan); /* kernels one plan_launch enqueues */
+/* Pinned (page-locked, device-mapped) host memory for the caller's input / output buffers, so that a host
+ * language without CUDA bindings (the cgo facade) reaches lzgpu_decode_batch's fast path: compressed input read
+ * by the kernel straight from host memory, output streamed back while it runs.  NULL on failure (no device,
+ * out of memory); lzgpu_last_error() says why.  Buffers from elsewhere (Go slices, malloc) still work: they
+ * are staged through device slabs. */
+void *lzgpu_alloc_pinned(uint64_t size);
+void lzgpu_free_pinned(void *p);
+
 /* On-device verification (no reference analogue): CRC-32 (zlib's crc32, the .xz
  * CHECK_CRC32 polynomial) of every unit's decoded bytes out[out_off, out_off + bytes_out), computed on the
  * GPU after plan_launch on the same stream and returned in crc[n_units] (host memory).  Units that did not

@@ -66,6 +66,8 @@ SYMBOLS = [
     ("lzgpu_plan_results", C.c_int, [_vp, C.POINTER(Result), C.POINTER(Stats)]),
     ("lzgpu_plan_launch_count", C.c_int, [_vp]),
     ("lzgpu_plan_crc32", C.c_int, [_vp, _u8p, C.POINTER(C.c_uint32)]),
+    ("lzgpu_alloc_pinned", C.c_void_p, [_u64]),
+    ("lzgpu_free_pinned", None, [_vp]),
     ("lzgpu_plan_destroy", None, [_vp]),
 ]
 

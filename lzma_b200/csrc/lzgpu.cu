@@ -533,6 +533,22 @@ extern "C" int lzgpu_plan_launch(lzgpu_plan *p, const uint8_t *d_in, uint8_t *d_
     return LZGPU_E_OK;
 }
 
+// ------------------------------------------------------------------ pinned buffers for callers without CUDA bindings
+extern "C" void *lzgpu_alloc_pinned(uint64_t size) {
+    if (lzgpu_device_count() <= 0) { fail(LZGPU_E_NO_DEVICE, "alloc_pinned: no CUDA device visible (" + g_last_error + ")"); return nullptr; }
+    void *p = nullptr;
+    const cudaError_t e = cudaHostAlloc(&p, size ? size : 1, cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fail(e == cudaErrorMemoryAllocation ? LZGPU_E_NOMEM : LZGPU_E_CUDA, std::string("alloc_pinned: ") + cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void lzgpu_free_pinned(void *p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ on-device verification
 // CRC-32 (IEEE 802.3, reflected 0xEDB88320: zlib's crc32, the .xz CHECK_CRC32) of every unit's decoded bytes,
 // so that a batch too large to copy back (BASELINE config 5: 64 GiB) is verified where it lies.

@@ -101,3 +101,6 @@ def test_no_device_means_hard_error():
     with pytest.raises(L.LzgpuError) as e:
         B.Context()
     assert e.value.code == L.E_NO_DEVICE and "no CPU" in str(e.value)
+    assert not lib.lzgpu_alloc_pinned(4096)             # pinned buffers need a device too
+    assert b"no CUDA device" in lib.lzgpu_last_error()
+    lib.lzgpu_free_pinned(None)

@@ -219,6 +219,27 @@ def test_pinned_host_buffers(ctx, shift, monkeypatch):
     assert res[n + 1].status == L.OK_INPUT_EXHAUSTED
 
 
+def test_library_pinned_buffers(ctx):
+    """lzgpu_alloc_pinned: what a cgo caller uses for its buffers; the batch call takes the zero-copy route on them."""
+    lib = L.lib()
+    plains = [K.text_block(2100 + i, 700_000) for i in range(3)]
+    streams = [K.compress_alone(p) for p in plains] * 16
+    units, in_np, out_size, _ = B.build_alone_batch(streams, [700_000] * len(streams))
+    p_in, p_out = lib.lzgpu_alloc_pinned(in_np.size), lib.lzgpu_alloc_pinned(out_size)
+    assert p_in and p_out
+    try:
+        a_in = np.ctypeslib.as_array(C.cast(p_in, C.POINTER(C.c_uint8)), (in_np.size,))
+        a_out = np.ctypeslib.as_array(C.cast(p_out, C.POINTER(C.c_uint8)), (out_size,))
+        a_in[:] = in_np
+        res, st = ctx.decode_batch(units, a_in, a_out)
+        assert st.h2d_ms < 0.5          # nothing was copied ahead of the kernel
+        for k, (r, u) in enumerate(zip(res, units)):
+            assert r.status == L.OK and a_out[u.out_off:u.out_off + r.bytes_out].tobytes() == plains[k % 3], k
+    finally:
+        lib.lzgpu_free_pinned(p_in)
+        lib.lzgpu_free_pinned(p_out)
+
+
 def test_large_literal_tables_in_hbm(ctx):
     """lc+lp > 4 needs literal tables beyond shared memory (the reference accepts any prop < 225,
     reader1.go:210-221).  liblzma cannot write such streams, so build one by re-labelling: a stream
