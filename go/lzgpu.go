@@ -63,7 +63,8 @@ func (e *Engine) Close() { C.lzgpu_ctx_destroy(e.ctx); e.ctx = nil }
 
 // PinnedBuffer is host memory the GPUs can address (lzgpu_alloc_pinned): input placed in one is read by the
 // decode kernel directly over PCIe, output written to one is streamed back while the kernel runs.
-// DecodeBatch uses pinned scratch buffers internally; callers with long-lived buffers can hold their own.
+// DecodeBatch above lays its units into ordinary Go slices (staged through device slabs by the library); a caller
+// with long-lived buffers holds PinnedBuffers and passes their .B to lzgpu_decode_batch for the zero-copy path.
 type PinnedBuffer struct {
 	p unsafe.Pointer
 	B []byte
