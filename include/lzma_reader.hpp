@@ -115,6 +115,27 @@ class Engine {
     lzgpu_ctx *ctx_ = nullptr;
 };
 
+// decoded bytes of a reader: page-locked memory (lzgpu_alloc_pinned) when large, so that the batch call streams
+// them back while the kernel runs; ordinary memory otherwise or when pinning fails
+class Bytes {
+  public:
+    Bytes() = default;
+    Bytes(const Bytes &) = delete;
+    Bytes &operator=(const Bytes &) = delete;
+    ~Bytes() { release(); }
+    void reset(size_t n);                    // contents undefined afterwards
+    void truncate(size_t n) { if (n < size_) size_ = n; }
+    void clear() { size_ = 0; }
+    uint8_t *data() { return p_; }
+    const uint8_t *data() const { return p_; }
+    size_t size() const { return size_; }
+  private:
+    void release();
+    uint8_t *p_ = nullptr;
+    size_t size_ = 0, cap_ = 0;
+    bool pinned_ = false;
+};
+
 // ---- reader1.go ---------------------------------------------------------------------------------
 std::tuple<uint8_t, uint8_t, uint8_t, error> DecodeProp(uint8_t d);        // (lc, pb, lp, err)
 std::pair<uint32_t, error> DecodeDictSize(const uint8_t properties[4]);
@@ -140,7 +161,8 @@ class Reader1 : public io::Reader {
     uint8_t lc_ = 0, lp_ = 0, pb_ = 0;
     uint32_t dict_ = 0;
     uint64_t unpack_ = ~0ull;
-    std::vector<uint8_t> payload_, out_;
+    std::vector<uint8_t> payload_;
+    Bytes out_;
     size_t pos_ = 0;
     bool decoded_ = false;
     error err_;
@@ -169,7 +191,8 @@ class Reader2 : public io::Reader {
     io::Reader *in_ = nullptr;
     std::shared_ptr<Engine> eng_;
     uint32_t dict_ = 0;
-    std::vector<uint8_t> buf_, out_;
+    std::vector<uint8_t> buf_;
+    Bytes out_;
     size_t rd_ = 0, pos_ = 0;
     bool in_eof_ = false, last_ = false, decoded_ = false;
     error err_;

@@ -34,6 +34,23 @@ class UnitResult:
         return self.status in (L.OK, L.OK_INPUT_EXHAUSTED)
 
 
+def pinned_empty(n: int) -> np.ndarray:
+    """uint8 array in page-locked host memory (lzgpu_alloc_pinned): buffers of this kind take the batch call's
+    zero-copy / streamed route.  Falls back to ordinary memory when pinning fails (the call still works)."""
+    import weakref
+    n = max(int(n), 1)
+    p = L.lib().lzgpu_alloc_pinned(n)
+    if not p:
+        return np.empty(n, dtype=np.uint8)
+    carr = (C.c_uint8 * n).from_address(p)
+    weakref.finalize(carr, L.lib().lzgpu_free_pinned, p)
+    return np.frombuffer(carr, dtype=np.uint8)
+
+
+def _out_buffer(n: int) -> np.ndarray:
+    return pinned_empty(n) if n >= (32 << 20) else np.empty(max(n, 16), dtype=np.uint8)
+
+
 def _ptr(a: np.ndarray) -> int:
     return a.ctypes.data
 
@@ -208,7 +225,7 @@ def decode_alone_streams(ctx: Context, streams: Sequence[bytes], out_caps: Seque
     for _ in range(max_retries + 1):
         sub = [streams[i] for i in todo]
         units, in_buf, out_size, _ = build_alone_batch(sub, [caps[i] for i in todo] if caps else None, ratio)
-        out_buf = np.empty(out_size, dtype=np.uint8)
+        out_buf = _out_buffer(out_size)
         res, _st = ctx.decode_batch(units, in_buf, out_buf)
         nxt = []
         for k, i in enumerate(todo):
@@ -231,7 +248,7 @@ def decode_lzma2_stream(ctx: Context, data: bytes, dict_size: int = 0):
     have delivered them."""
     units, total, sst = scan_lzma2(data, dict_size)
     in_buf = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(1, dtype=np.uint8)
-    out_buf = np.empty(max(total, 16), dtype=np.uint8)
+    out_buf = _out_buffer(max(total, 16))
     res, _ = ctx.decode_batch(units, in_buf, out_buf)
     n_out = 0
     for u, r in zip(units, res):

@@ -4,8 +4,10 @@
 #include "lzma_reader.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <new>
 
 namespace lzma {
 
@@ -126,6 +128,30 @@ size_t read_exact(io::Reader *r, uint8_t *p, size_t n) {
 }
 }  // namespace
 
+// ---------------------------------------------------------------- Bytes
+void Bytes::release() {
+    if (p_) {
+        if (pinned_) lzgpu_free_pinned(p_);
+        else free(p_);
+    }
+    p_ = nullptr;
+    size_ = cap_ = 0;
+    pinned_ = false;
+}
+void Bytes::reset(size_t n) {
+    if (n <= cap_) { size_ = n; return; }
+    release();
+    const size_t want = std::max<size_t>(n, 16);
+    if (want >= (32u << 20)) {
+        p_ = static_cast<uint8_t *>(lzgpu_alloc_pinned(want));
+        pinned_ = p_ != nullptr;
+    }
+    if (!p_) p_ = static_cast<uint8_t *>(malloc(want));
+    if (!p_) throw std::bad_alloc();
+    cap_ = want;
+    size_ = n;
+}
+
 // ---------------------------------------------------------------- engine
 std::pair<std::shared_ptr<Engine>, error> Engine::New(const std::vector<int> &devices) {
     std::shared_ptr<Engine> e(new Engine());
@@ -215,7 +241,7 @@ void Reader1::decode() {
     for (;;) {
         u.out_off = 0;
         u.out_cap = cap;
-        out_.resize((size_t)std::max<uint64_t>(cap, 16));
+        out_.reset((size_t)std::max<uint64_t>(cap, 16));
         auto [res, err] = eng_->DecodeBatch({u}, payload_.data(), payload_.size(), out_.data(), out_.size());
         if (err) { out_.clear(); err_ = err; return; }
         const bool can_grow = known ? cap < unpack_ : cap < (1ull << 40);
@@ -223,7 +249,7 @@ void Reader1::decode() {
             cap = known ? std::min<uint64_t>(cap * 8, unpack_) : cap * 8;
             continue;
         }
-        out_.resize((size_t)res[0].bytes_out);
+        out_.truncate((size_t)res[0].bytes_out);
         err_ = Engine::StatusError(res[0].status);
         break;
     }
@@ -423,7 +449,7 @@ void Reader2::decodeWave() {
     }
     if (n < 0) { err_ = errors::New(std::string("lzgpu: ") + lzgpu_last_error()); last_ = true; return; }
     units.resize((size_t)n);
-    out_.resize((size_t)std::max<uint64_t>(total, 16));
+    out_.reset((size_t)std::max<uint64_t>(total, 16));
     auto [res, err] = eng_->DecodeBatch(units, wave.data(), wave.size(), out_.data(), out_.size());
     if (err) { out_.clear(); err_ = err; last_ = true; return; }
     // the bytes of the units before the first failing one are delivered with the failure, as the reference's
@@ -434,7 +460,7 @@ void Reader2::decodeWave() {
         n_out = units[k].out_off + res[k].bytes_out;
         if (res[k].status != LZGPU_OK) { status = res[k].status; break; }
     }
-    out_.resize((size_t)n_out);
+    out_.truncate((size_t)n_out);
     err_ = Engine::StatusError(status);
     last_ = last || err_ != nullptr;
 }

@@ -241,6 +241,26 @@ static void TestReader2WithFileVerification() {   // reader2_test.go:12-29
     MD5 s2;
     auto [n2, e3] = io::Copy(s2, *r2);
     REQUIRE(!e3 && n2 == n && s2.Sum() == randomFileMD5, "waves of one unit");
+    // a long stream: the asset 40 times over (each copy starts with a dictionary reset -> 40 units in one wave,
+    // 40 MiB of output: the reader's buffer is page-locked and the batch call streams into it)
+    {
+        Collect plain;
+        io::BytesReader in4(compressedData);
+        auto [r4, e6] = NewReader2(in4, 0);
+        REQUIRE(!e6, text(e6));
+        REQUIRE(!io::Copy(plain, *r4).second && plain.v.size() == (size_t)n, "plaintext of the asset");
+        std::vector<uint8_t> big;
+        for (int k = 0; k < 40; k++) big.insert(big.end(), compressedData.begin(), compressedData.end() - 1);
+        big.push_back(0);
+        io::BytesReader in5(big);
+        auto [r5, e7] = NewReader2(in5, 0);
+        REQUIRE(!e7, text(e7));
+        MD5 got, want;
+        auto [n5, e8] = io::Copy(got, *r5);
+        for (int k = 0; k < 40; k++) want.Write(plain.v.data(), plain.v.size());
+        REQUIRE(!e8 && n5 == 40 * n && got.Sum() == want.Sum(), "40 MiB LZMA2 stream");
+        printf("ok   TestReader2 long stream (%lld bytes)\n", (long long)n5);
+    }
     // truncated stream: io.ErrUnexpectedEOF after the bytes of the complete chunks
     io::BytesReader in3(compressedData.data(), compressedData.size() - 1);   // terminator cut off
     auto [r3, e4] = NewReader2(in3, 0);
