@@ -75,6 +75,11 @@ enum lzgpu_kind {
 #define LZGPU_UF_LZMA2_LAST 1u    /* last unit of its stream: must end with a terminator, else UNEXPECTED_EOF */
 #define LZGPU_UF_LZMA2_FRESH 2u   /* no LZMA chunk precedes this unit in its stream: the first LZMA chunk
                                      builds a new coder whatever its control byte says (reader2.go:146-153) */
+#define LZGPU_UF_BITS_KNOWN 4u    /* LZMA2: lit_bits / pos_bits below were computed from the chunk headers
+                                     (lzgpu_scan_lzma2 sets it).  Without it lzgpu_decode_batch walks the unit's
+                                     chunk headers itself, so a binding that drops the two fields cannot make a
+                                     unit fail; lzgpu_plan_create (input already on the device) takes lit_bits
+                                     as given and assumes pos_bits = 4 */
 
 typedef struct lzgpu_unit {
     uint64_t in_off, in_len;    /* compressed bytes: [in_off, in_off+in_len) of the batch input buffer */
@@ -84,8 +89,11 @@ typedef struct lzgpu_unit {
     uint32_t dict_size;         /* dictionary size in bytes (after the reference's clamping) */
     uint8_t kind;               /* enum lzgpu_kind */
     uint8_t lc, lp, pb;         /* LZMA1: literal/pos bits.  LZMA2: props in force before the unit */
-    uint8_t lit_bits;           /* max lc+lp any chunk of the unit uses (sizes the literal tables) */
-    uint8_t pad8[3];
+    uint8_t lit_bits;           /* LZMA2: max lc+lp any chunk of the unit uses (sizes the literal tables);
+                                   LZMA1: ignored (lc + lp) */
+    uint8_t pos_bits;           /* LZMA2: max pb any chunk of the unit uses (sizes the posState-indexed tables);
+                                   LZMA1: ignored (pb) */
+    uint8_t pad8[2];
     uint32_t flags;             /* LZGPU_UF_* */
     uint64_t user;              /* caller's tag, copied to nothing; keeps the struct at 64 bytes */
 } lzgpu_unit;

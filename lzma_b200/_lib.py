@@ -21,13 +21,13 @@ E_OK, E_NO_DEVICE, E_CUDA, E_INVALID, E_NOMEM = 0, -1, -2, -3, -4
 # enum lzgpu_kind
 KIND_LZMA1_ALONE, KIND_LZMA1_RAW, KIND_LZMA2_GROUP = 0, 1, 2
 UNKNOWN_SIZE = (1 << 64) - 1
-UF_LZMA2_LAST, UF_LZMA2_FRESH = 1, 2
+UF_LZMA2_LAST, UF_LZMA2_FRESH, UF_BITS_KNOWN = 1, 2, 4
 
 
 class Unit(C.Structure):
     _fields_ = [("in_off", C.c_uint64), ("in_len", C.c_uint64), ("out_off", C.c_uint64), ("out_cap", C.c_uint64),
                 ("unpack_size", C.c_uint64), ("dict_size", C.c_uint32), ("kind", C.c_uint8), ("lc", C.c_uint8),
-                ("lp", C.c_uint8), ("pb", C.c_uint8), ("lit_bits", C.c_uint8), ("pad8", C.c_uint8 * 3),
+                ("lp", C.c_uint8), ("pb", C.c_uint8), ("lit_bits", C.c_uint8), ("pos_bits", C.c_uint8), ("pad8", C.c_uint8 * 2),
                 ("flags", C.c_uint32), ("user", C.c_uint64)]
 
 

@@ -45,13 +45,13 @@ struct KArgs {
 // One warp per CTA, one unit per warp.  Fixed tables (3.7 KB) always in shared
 // memory; literal tables in shared memory when lc+lp <= 4 (<= 24 KB), else in HBM.
 template <bool kLitGlobal, int kV>
-__global__ void __launch_bounds__(32, 8) lzgpu_decode_kernel(const KArgs a) {
+__global__ void __launch_bounds__(32, 14) lzgpu_decode_kernel(const KArgs a) {
     extern __shared__ __align__(16) uint16_t smem_probs[];
     const uint32_t slot = a.slot0 + blockIdx.x;
     const int32_t ui = a.order[slot];
     const lzgpu_unit u = a.units[ui];
     uint16_t *P = smem_probs;
-    uint16_t *L = kLitGlobal ? a.lit_ws + (size_t)blockIdx.x * a.lit_ws_stride : smem_probs + P_LIT;
+    uint16_t *L = kLitGlobal ? a.lit_ws + (size_t)blockIdx.x * a.lit_ws_stride : smem_probs + LZ_LAY(kV)::LIT;
     UnitIO io;
     io.in = a.in_base + u.in_off;
     io.in_len = u.in_len;
@@ -73,17 +73,22 @@ static int decoder_variant() {
     return LZGPU_DEFAULT_VARIANT;
 }
 
+// pb2: the launch's units all have pb <= 2 -> the instantiation with compact posState tables (V_PB2, Lay<2>).
 template <bool kLitGlobal>
-static void launch_decode(int variant, unsigned grid, size_t smem, cudaStream_t st, const KArgs &a) {
+static void launch_decode(int variant, bool pb2, unsigned grid, size_t smem, cudaStream_t st, const KArgs &a) {
     if (kLitGlobal && (variant & V_CHAIN)) variant = 1;   // V_CHAIN needs its literal tables in shared memory
+    if (kLitGlobal) pb2 = false;                          // (rare class: one layout is enough)
+#define LZ_LAUNCH(V)                                                                                      \
+    do {                                                                                                  \
+        if (pb2) lzgpu_decode_kernel<kLitGlobal, kLitGlobal ? (V) : ((V) | V_PB2)><<<grid, 32, smem, st>>>(a);   \
+        else lzgpu_decode_kernel<kLitGlobal, (V)><<<grid, 32, smem, st>>>(a);                             \
+    } while (0)
     switch (variant) {
-        case 33: lzgpu_decode_kernel<kLitGlobal, kLitGlobal ? 1 : 33><<<grid, 32, smem, st>>>(a); break;
-        case 0: lzgpu_decode_kernel<kLitGlobal, 0><<<grid, 32, smem, st>>>(a); break;
-        case 5: lzgpu_decode_kernel<kLitGlobal, 5><<<grid, 32, smem, st>>>(a); break;
-        case 17: lzgpu_decode_kernel<kLitGlobal, 17><<<grid, 32, smem, st>>>(a); break;
-        case 21: lzgpu_decode_kernel<kLitGlobal, 21><<<grid, 32, smem, st>>>(a); break;
-        default: lzgpu_decode_kernel<kLitGlobal, 1><<<grid, 32, smem, st>>>(a); break;
+        case 33: LZ_LAUNCH(kLitGlobal ? 1 : 33); break;
+        case 0: LZ_LAUNCH(0); break;
+        default: LZ_LAUNCH(1); break;
     }
+#undef LZ_LAUNCH
 }
 
 // ------------------------------------------------------------------ errors
@@ -186,7 +191,8 @@ extern "C" int64_t lzgpu_scan_lzma2(const uint8_t *in, uint64_t in_len, uint32_t
         cur.lp = (uint8_t)((p / 9) % 5);
         cur.pb = (uint8_t)((p / 9) / 5);
         cur.lit_bits = 0;
-        cur.flags = seen_lzma ? 0u : LZGPU_UF_LZMA2_FRESH;
+        cur.pos_bits = 0;
+        cur.flags = (seen_lzma ? 0u : LZGPU_UF_LZMA2_FRESH) | LZGPU_UF_BITS_KNOWN;
     };
     auto close_unit = [&](uint64_t end, bool last) {
         cur.in_len = end - cur.in_off;
@@ -237,8 +243,9 @@ extern "C" int64_t lzgpu_scan_lzma2(const uint8_t *in, uint64_t in_len, uint32_t
         if (c >= 0xC0) props = in[pos + 5];
         if (c >= 0x80) {
             if (props < 225) {
-                const uint32_t lb = props % 9 + (props / 9) % 5;
+                const uint32_t lb = props % 9 + (props / 9) % 5, pbits = (props / 9) / 5;
                 if (lb > cur.lit_bits) cur.lit_bits = (uint8_t)lb;
+                if (pbits > cur.pos_bits) cur.pos_bits = (uint8_t)pbits;
             }
             seen_lzma = true;
         }
@@ -286,6 +293,9 @@ struct DevState {
     // call (cudaMalloc / cudaFree serialise against the other GPUs' work in a multi-GPU process: 12 ms seen)
     uint8_t *d_desc = nullptr;
     uint64_t desc_cap = 0;
+    // per-unit checksums of lzgpu_plan_crc32 / lzgpu_plan_crc64 (grow-only, for the same reason)
+    uint8_t *d_sum = nullptr;
+    uint64_t sum_cap = 0;
 };
 
 struct lzgpu_ctx {
@@ -296,6 +306,7 @@ struct lzgpu_ctx {
 struct Launch {
     uint32_t lit_bits;   // class
     bool lit_global;
+    bool pb2;            // compact posState tables (every unit of the launch has pb <= 2)
     uint32_t slot0, count;
     size_t smem;
 };
@@ -353,6 +364,7 @@ extern "C" void lzgpu_ctx_destroy(lzgpu_ctx *c) {
         if (d.h_progress) cudaFreeHost(d.h_progress);
         if (d.h_tails) cudaFreeHost(d.h_tails);
         if (d.d_desc) cudaFree(d.d_desc);
+        if (d.d_sum) cudaFree(d.d_sum);
         if (d.d_in) cudaFree(d.d_in);
         if (d.d_out) cudaFree(d.d_out);
     }
@@ -376,11 +388,11 @@ extern "C" void lzgpu_plan_destroy(lzgpu_plan *p) {
 }
 
 // shared memory of one unit: probability tables, 2 x 64 bytes of window-copy staging, the V_CHAIN input stage
-static size_t probs_elems(uint32_t lit_bits, bool lit_global) {
-    return (size_t)P_FIXED + (lit_global ? 0 : ((size_t)0x300 << lit_bits));
+static size_t probs_elems(uint32_t lit_bits, bool lit_global, bool pb2) {
+    return (size_t)(pb2 && !lit_global ? Lay<2>::FIXED : Lay<4>::FIXED) + (lit_global ? 0 : ((size_t)0x300 << lit_bits));
 }
-static size_t smem_bytes(uint32_t lit_bits, bool lit_global) {
-    return sizeof(uint16_t) * probs_elems(lit_bits, lit_global) + 128 + kF2Stage;
+static size_t smem_bytes(uint32_t lit_bits, bool lit_global, bool pb2) {
+    return sizeof(uint16_t) * probs_elems(lit_bits, lit_global, pb2) + 128 + kF2Stage;
 }
 
 static int plan_create_impl(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *units, int64_t n,
@@ -424,10 +436,12 @@ static int plan_create_impl(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *uni
         if (!run) continue;
         runnable.push_back((int32_t)i);
     }
-    // launch order: by literal-table class, then longest compressed input first (LPT within the GPU)
+    // launch order: by table class (literal-table size; posState tables compact or full), then longest
+    // compressed input first (LPT within the GPU)
+    auto cls = [](const lzgpu_unit &u) -> uint32_t { return u.lit_bits <= 4 ? 2u * u.lit_bits + (u.pos_bits > 2 ? 1u : 0u) : 100u; };
     std::stable_sort(runnable.begin(), runnable.end(), [&](int32_t a, int32_t b) {
         const lzgpu_unit &x = p->units[(size_t)a], &y = p->units[(size_t)b];
-        const uint32_t cx = x.lit_bits <= 4 ? x.lit_bits : 100, cy = y.lit_bits <= 4 ? y.lit_bits : 100;
+        const uint32_t cx = cls(x), cy = cls(y);
         if (cx != cy) return cx < cy;
         return x.in_len > y.in_len;
     });
@@ -442,7 +456,7 @@ static int plan_create_impl(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *uni
         uint32_t maxbits = 0;
         while (e < runnable.size()) {
             const lzgpu_unit &ue = p->units[(size_t)runnable[e]];
-            if (g ? ue.lit_bits <= 4 : ue.lit_bits != u0.lit_bits) break;
+            if (g ? ue.lit_bits <= 4 : cls(ue) != cls(u0)) break;
             maxbits = std::max<uint32_t>(maxbits, ue.lit_bits);
             e++;
         }
@@ -453,11 +467,12 @@ static int plan_create_impl(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *uni
             ws_bits = std::max(ws_bits, maxbits);
             for (uint32_t w = s; w < e; w += (uint32_t)max_slots) {
                 const uint32_t cnt = (uint32_t)std::min<uint64_t>(max_slots, e - w);
-                p->launches.push_back({maxbits, true, w, cnt, smem_bytes(maxbits, true)});
+                p->launches.push_back({maxbits, true, false, w, cnt, smem_bytes(maxbits, true, false)});
                 ws_slots = std::max<uint64_t>(ws_slots, cnt);
             }
         } else {
-            p->launches.push_back({maxbits, false, s, e - s, smem_bytes(maxbits, false)});
+            const bool pb2 = u0.pos_bits <= 2;
+            p->launches.push_back({maxbits, false, pb2, s, e - s, smem_bytes(maxbits, false, pb2)});
         }
         s = e;
     }
@@ -521,16 +536,29 @@ extern "C" int lzgpu_plan_launch(lzgpu_plan *p, const uint8_t *d_in, uint8_t *d_
         a.lit_ws_stride = p->lit_ws_stride;
         a.lit_bits_cap = L.lit_bits;
         a.slot0 = L.slot0;
-        a.stage_off = (uint32_t)probs_elems(L.lit_bits, L.lit_global);
+        a.stage_off = (uint32_t)probs_elems(L.lit_bits, L.lit_global, L.pb2);
         a.progress = p->d_progress;
-        if (L.lit_global) launch_decode<true>(p->variant, L.count, L.smem, st, a);
-        else launch_decode<false>(p->variant, L.count, L.smem, st, a);
+        if (L.lit_global) launch_decode<true>(p->variant, false, L.count, L.smem, st, a);
+        else launch_decode<false>(p->variant, L.pb2, L.count, L.smem, st, a);
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaEventRecord(p->ev1, st));
     p->last_stream = st;
     p->launched = true;
     return LZGPU_E_OK;
+}
+
+// grow-only device buffer: 0 ok, -1 out of memory
+static int ensure(uint8_t *&ptr, uint64_t &cap, uint64_t need) {
+    if (need <= cap) return 0;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    const uint64_t want = need + (need >> 3) + 4096;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+    cap = want;
+    return 0;
 }
 
 // ------------------------------------------------------------------ pinned buffers for callers without CUDA bindings
@@ -640,14 +668,13 @@ extern "C" int lzgpu_plan_crc32(lzgpu_plan *p, const uint8_t *d_out, uint32_t *c
     if (p->n == 0) return LZGPU_E_OK;
     DevState &ds = p->ctx->devs[p->dev_index];
     CUDA_TRY(cudaSetDevice(ds.device));
-    uint32_t *d_crc = nullptr;
-    CUDA_TRY(cudaMalloc(&d_crc, sizeof(uint32_t) * (size_t)p->n));
+    if (ensure(ds.d_sum, ds.sum_cap, sizeof(uint32_t) * (uint64_t)p->n)) return fail(LZGPU_E_NOMEM, "plan_crc32: cudaMalloc of the checksum array failed");
+    uint32_t *d_crc = reinterpret_cast<uint32_t *>(ds.d_sum);
     const unsigned grid = (unsigned)std::min<int64_t>(p->n, 148 * 16);
     lzgpu_crc32_kernel<<<grid, 256, 0, p->last_stream>>>(p->d_units, p->d_results, d_out, d_crc, p->n);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(crc, d_crc, sizeof(uint32_t) * (size_t)p->n, cudaMemcpyDeviceToHost, p->last_stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(p->last_stream);
-    cudaFree(d_crc);
     if (e != cudaSuccess) return fail(LZGPU_E_CUDA, std::string("plan_crc32: ") + cudaGetErrorString(e));
     return LZGPU_E_OK;
 }
@@ -699,21 +726,23 @@ struct Shard {
 
 // Coalesce [off, off+len) ranges (sorted by off) into few large copies; returns the
 // device offset of each range.
+// `gap`: ranges closer than this are merged into one copy.  Output ranges are merged only when they touch
+// (gap 0): a D2H copy of a merged run writes every byte between its ends, and bytes of the caller's buffer
+// that belong to no unit of this shard (padding, or another GPU's units) must stay untouched.
 void layout_ranges(const std::vector<std::pair<uint64_t, uint64_t>> &ranges, std::vector<uint64_t> &dev_off,
-                   std::vector<Shard::Run> &runs, uint64_t &total) {
+                   std::vector<Shard::Run> &runs, uint64_t &total, uint64_t gap) {
     const size_t n = ranges.size();
     std::vector<size_t> ord(n);
     std::iota(ord.begin(), ord.end(), 0);
     std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return ranges[a].first < ranges[b].first; });
     dev_off.assign(n, 0);
     total = 0;
-    const uint64_t kGap = 64 << 10;
     for (size_t k = 0; k < n; k++) {
         const auto &r = ranges[ord[k]];
         if (!runs.empty()) {
             Shard::Run &last = runs.back();
             const uint64_t last_end = last.host_off + last.len;
-            if (r.first <= last_end + kGap) {
+            if (r.first <= last_end + gap) {
                 const uint64_t new_end = std::max(last_end, r.first + r.second);
                 dev_off[ord[k]] = last.dev_off + (r.first - last.host_off);
                 last.len = new_end - last.host_off;
@@ -728,18 +757,6 @@ void layout_ranges(const std::vector<std::pair<uint64_t, uint64_t>> &ranges, std
         dev_off[ord[k]] = d;
         total = d + r.second;
     }
-}
-
-int ensure(uint8_t *&ptr, uint64_t &cap, uint64_t need) {
-    if (need <= cap) return 0;
-    if (ptr) cudaFree(ptr);
-    ptr = nullptr;
-    cap = 0;
-    const uint64_t want = need + (need >> 3) + 4096;
-    cudaError_t e = cudaMalloc(&ptr, want);
-    if (e != cudaSuccess) { cudaGetLastError(); return -1; }
-    cap = want;
-    return 0;
 }
 
 // Pinned (device-accessible) host memory under unified addressing: the device pointer of [p, p + len), else null.
@@ -803,8 +820,8 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
     const uint8_t *zc_in = getenv("LZGPU_NO_ZEROCOPY_IN") ? nullptr : device_view_of_host(in_base, in_size);
     uint8_t *zc_out = getenv("LZGPU_NO_TAIL_KERNEL") ? nullptr : const_cast<uint8_t *>(device_view_of_host(out_base, out_size));
     if (zc_in) sh.in_bytes = in_size;
-    else layout_ranges(ir, ioff, sh.in_runs, sh.in_bytes);
-    layout_ranges(orr, ooff, sh.out_runs, sh.out_bytes);
+    else layout_ranges(ir, ioff, sh.in_runs, sh.in_bytes, 64 << 10);
+    layout_ranges(orr, ooff, sh.out_runs, sh.out_bytes, 0);
     for (size_t k = 0; k < n; k++) { if (!zc_in) sh.units[k].in_off = ioff[k]; sh.units[k].out_off = ooff[k]; }
     if ((!zc_in && ensure(ds.d_in, ds.in_cap, sh.in_bytes + 16)) || ensure(ds.d_out, ds.out_cap, sh.out_bytes + 16)) {
         sh.rc = LZGPU_E_NOMEM;
@@ -860,74 +877,105 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
     }
     cudaEventRecord(e2, ds.stream);
     mark("kernel enqueued");
+    // Only the bytes a unit decoded go back to the caller (not its whole capacity: what lies behind bytes_out
+    // in the device slab is left over from earlier batches), so the final copies wait for the results.
+    std::vector<uint32_t> copied(n, 0);      // streamed: 64 KiB blocks of unit k already sent
+    auto send = [&](size_t k, uint64_t from, uint64_t to) {   // bytes [from, to) of unit k's output
+        if (to <= from || sh.rc != 0) return;
+        cudaError_t ce = cudaMemcpyAsync(out_base + host_out_off[k] + from, ds.d_out + sh.units[k].out_off + from, to - from,
+                                         cudaMemcpyDeviceToHost, ds.copy_stream);
+        if (ce != cudaSuccess) cuda_fail(ce, "D2H (streamed)");
+    };
     if (sh.rc == 0 && stream_out) {
-        std::vector<uint32_t> copied(n, 0);
         volatile const uint32_t *prog = ds.h_progress;
-        auto send = [&](size_t k, uint64_t from, uint64_t to) {   // bytes [from, to) of unit k's output
-            if (to <= from || sh.rc != 0) return;
-            cudaError_t ce = cudaMemcpyAsync(out_base + host_out_off[k] + from, ds.d_out + sh.units[k].out_off + from, to - from,
-                                             cudaMemcpyDeviceToHost, ds.copy_stream);
-            if (ce != cudaSuccess) cuda_fail(ce, "D2H (streamed)");
-        };
+        int idle = 0;
         for (;;) {
             const cudaError_t q = cudaEventQuery(e2);
             if (q != cudaErrorNotReady) { if (q != cudaSuccess) cuda_fail(q, "decode kernel"); break; }
+            bool progressed = false;
             for (size_t k = 0; k < n && sh.rc == 0; k++) {
                 const uint32_t have = prog[k];
                 if (have > copied[k]) {
                     const uint64_t cap = sh.units[k].out_cap;
                     send(k, std::min<uint64_t>(copied[k] * kBlock, cap), std::min<uint64_t>(have * kBlock, cap));
                     copied[k] = have;
+                    progressed = true;
                 }
             }
             if (sh.rc != 0) break;
+            // a 1 MiB unit finishes a block every ~7 ms: nothing is lost by sleeping between scans, and the
+            // host core is free for the caller (or for the other GPUs' shard threads)
+            if (progressed) idle = 0;
+            else if (++idle > 2) std::this_thread::sleep_for(std::chrono::microseconds(100));
         }
-        if (zc_out && sh.rc == 0) {
+    }
+    std::vector<lzgpu_result> tmp(n);
+    lzgpu_stats st;
+    memset(&st, 0, sizeof st);
+    if (sh.rc == 0) {
+        rc = lzgpu_plan_results(plan, tmp.data(), &st);   // waits for the kernel
+        if (rc != LZGPU_E_OK) { sh.rc = rc; sh.err = g_last_error; }
+    }
+    if (sh.rc == 0 && stream_out) {
+        if (zc_out) {
             // the tails, by ONE kernel that writes the caller's (pinned) buffer over PCIe: a thousand small
             // cudaMemcpyAsync calls cost more host time than the bytes take to move
             for (size_t k = 0; k < n; k++) {
-                const uint64_t cap = sh.units[k].out_cap, from = std::min<uint64_t>(copied[k] * kBlock, cap);
+                const uint64_t done = std::min<uint64_t>(tmp[k].bytes_out, sh.units[k].out_cap), from = std::min<uint64_t>(copied[k] * kBlock, done);
                 ds.h_tails[3 * k] = sh.units[k].out_off + from;
                 ds.h_tails[3 * k + 1] = host_out_off[k] + from;
-                ds.h_tails[3 * k + 2] = cap - from;
+                ds.h_tails[3 * k + 2] = done - from;
             }
             lzgpu_tail_copy_kernel<<<dim3((unsigned)n, 2), 256, 0, ds.copy_stream>>>(ds.d_tails, ds.d_out, zc_out);
             const cudaError_t ce = cudaGetLastError();
             if (ce != cudaSuccess) cuda_fail(ce, "tail copy kernel");
-        } else
-        for (size_t k = 0; k < n && sh.rc == 0; k++)           // the tails
-            send(k, std::min<uint64_t>(copied[k] * kBlock, sh.units[k].out_cap), sh.units[k].out_cap);
+        } else {
+            for (size_t k = 0; k < n && sh.rc == 0; k++) {
+                const uint64_t done = std::min<uint64_t>(tmp[k].bytes_out, sh.units[k].out_cap);
+                send(k, std::min<uint64_t>(copied[k] * kBlock, done), done);
+            }
+        }
         mark("kernel finished, tails enqueued");
         cudaEventRecord(e3, ds.copy_stream);
         e = cudaStreamSynchronize(ds.copy_stream);
         if (e != cudaSuccess && sh.rc == 0) cuda_fail(e, "D2H (streamed) sync");
     } else {
-    if (sh.rc == 0) {
-        for (const auto &r : sh.out_runs) {
-            e = cudaMemcpyAsync(out_base + r.host_off, ds.d_out + r.dev_off, r.len, cudaMemcpyDeviceToHost, ds.stream);
-            if (e != cudaSuccess) { cuda_fail(e, "D2H"); break; }
+        if (sh.rc == 0) {
+            // one copy per run of units that are adjacent in the caller's buffer and filled to their capacity
+            std::vector<size_t> ord(n);
+            std::iota(ord.begin(), ord.end(), 0);
+            std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return host_out_off[a] < host_out_off[b]; });
+            uint64_t h0 = 0, d0 = 0, len = 0;
+            auto flush = [&]() {
+                if (len && sh.rc == 0) {
+                    e = cudaMemcpyAsync(out_base + h0, ds.d_out + d0, len, cudaMemcpyDeviceToHost, ds.stream);
+                    if (e != cudaSuccess) cuda_fail(e, "D2H");
+                }
+                len = 0;
+            };
+            for (size_t q = 0; q < n; q++) {
+                const size_t k = ord[q];
+                const uint64_t done = std::min<uint64_t>(tmp[k].bytes_out, sh.units[k].out_cap);
+                if (len && host_out_off[k] == h0 + len && sh.units[k].out_off == d0 + len) len += done;
+                else { flush(); h0 = host_out_off[k]; d0 = sh.units[k].out_off; len = done; }
+                if (done < sh.units[k].out_cap) flush();
+            }
+            flush();
         }
-    }
-    cudaEventRecord(e3, ds.stream);
+        cudaEventRecord(e3, ds.stream);
     }
     e = cudaStreamSynchronize(ds.stream);
     if (e != cudaSuccess && sh.rc == 0) cuda_fail(e, "decode kernel / stream sync");
     mark("streams idle");
     if (sh.rc == 0) {
-        std::vector<lzgpu_result> tmp(n);
-        lzgpu_stats st;
-        rc = lzgpu_plan_results(plan, tmp.data(), &st);
-        if (rc != LZGPU_E_OK) { sh.rc = rc; sh.err = g_last_error; }
-        else {
-            for (size_t k = 0; k < n; k++) results[sh.idx[k]] = tmp[k];
-            sh.kernel_ms = st.kernel_ms;
-            sh.launches = st.launches;
-            float a = 0, b = 0;
-            cudaEventElapsedTime(&a, e0, e1);
-            cudaEventElapsedTime(&b, e2, e3);
-            sh.h2d_ms = a;
-            sh.d2h_ms = b;
-        }
+        for (size_t k = 0; k < n; k++) results[sh.idx[k]] = tmp[k];
+        sh.kernel_ms = st.kernel_ms;
+        sh.launches = st.launches;
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, e0, e1);
+        cudaEventElapsedTime(&b, e2, e3);
+        sh.h2d_ms = a;
+        sh.d2h_ms = b;
     }
     mark("results read");
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
@@ -963,6 +1011,10 @@ extern "C" int lzgpu_decode_batch(lzgpu_ctx *ctx, const lzgpu_unit *units, int64
             // NewReader1 reads the 13-byte header eagerly (reader1.go:77-101)
             const int hs = lzgpu_parse_alone_header(in_base + u.in_off, u.in_len, &u);
             if (hs != LZGPU_OK) { results[i].status = hs; results[i].device = -1; continue; }
+        } else if (u.kind == LZGPU_KIND_LZMA2_GROUP && !(u.flags & LZGPU_UF_BITS_KNOWN)) {
+            // table sizes from the chunk headers themselves: a binding that does not carry lit_bits / pos_bits
+            // through (they are not part of any reference interface) cannot make the unit fail
+            derive_lzma2_bits(in_base, u);
         }
         Shard &s = shards[(size_t)shard_of[(size_t)i]];
         s.idx.push_back(i);

@@ -79,19 +79,28 @@ namespace lzgpu {
 
 // ---- probability-table layout, in uint16 units (Appendix A of SURVEY.md lists the
 // reference's tables: state.go:3-33).  isRep/G0/G1/G2 are interleaved per state.
-enum : uint32_t {
-    P_IS_MATCH = 0,        // [12][16]  (state<<4)+posState        decompress.go:23,26
-    P_IS_REP0_LONG = 192,  // [12][16]                              decompress.go:716
-    P_REP4 = 384,          // [12][4]   isRep, isRepG0, isRepG1, isRepG2 of one state
-    P_LEN0 = 432,          // match length coder (LEN_* below)      decompress.go:218-429
-    P_LEN1 = 952,          // rep length coder                      decompress.go:870-1118
-    P_POS_SLOT = 1472,     // [4][64]                               decompress.go:434-486
-    P_POS_DEC = 1728,      // [115] (+13 pad)                       decompress.go:491-546
-    P_ALIGN = 1856,        // [16]                                  decompress.go:580-625
-    P_LIT = 1872,          // 0x300 << (lc+lp)                      decompress.go:56-57
-    P_FIXED = 1872
+// The posState-indexed tables hold 1 << kPB positions: kPB = 4 fits every pb the reference
+// accepts (reader1.go:210-221); units whose pb is <= 2 (what xz / 7-zip write by default) run a
+// kernel instantiated with kPB = 2, whose fixed tables take 2 400 bytes instead of 3 744 -- with
+// lc+lp = 3 that is the difference between 13 and 14 units resident per SM.
+template <int kPB>
+struct Lay {
+    static constexpr uint32_t PB = kPB, NPS = 1u << kPB;
+    static constexpr uint32_t IS_MATCH = 0;                    // [12][NPS] (state<<kPB)+posState  decompress.go:23,26
+    static constexpr uint32_t IS_REP0_LONG = 12 * NPS;         // [12][NPS]                        decompress.go:716
+    static constexpr uint32_t REP4 = 24 * NPS;                 // [12][4] isRep, isRepG0, isRepG1, isRepG2 of one state
+    // one length coder: choice, choice2 (+6 pad), low [NPS][8], mid [NPS][8], high [256]
+    static constexpr uint32_t LEN_CHOICE = 0, LEN_CHOICE2 = 1, LEN_LOW = 8, LEN_MID = 8 + 8 * NPS,
+                              LEN_HIGH = 8 + 16 * NPS, LEN_SIZE = 8 + 16 * NPS + 256;
+    static constexpr uint32_t LEN0 = REP4 + 48;                // match length coder   decompress.go:218-429
+    static constexpr uint32_t LEN1 = LEN0 + LEN_SIZE;          // rep length coder     decompress.go:870-1118
+    static constexpr uint32_t POS_SLOT = LEN1 + LEN_SIZE;      // [4][64]              decompress.go:434-486
+    static constexpr uint32_t POS_DEC = POS_SLOT + 256;        // [115] (+13 pad)      decompress.go:491-546
+    static constexpr uint32_t ALIGN = POS_DEC + 128;           // [16]                 decompress.go:580-625
+    static constexpr uint32_t FIXED = ALIGN + 16;              // 1 872 (kPB 4) / 1 200 (kPB 2) cells
+    static constexpr uint32_t LIT = FIXED;                     // 0x300 << (lc+lp)     decompress.go:56-57
 };
-enum : uint32_t { LEN_CHOICE = 0, LEN_CHOICE2 = 1, LEN_LOW = 8, LEN_MID = 136, LEN_HIGH = 264, LEN_SIZE = 520 };
+static_assert(Lay<4>::FIXED == 1872 && Lay<2>::FIXED == 1200, "table layout");
 
 constexpr uint32_t kTop = 1u << 24;
 constexpr uint32_t kProbInit = 1024;
@@ -193,7 +202,10 @@ LZ_HD void rc_fill(Dec &d) {
 //               one predicated instruction, compressed input is staged in shared memory and read one
 //               byte ahead so that there are no lookahead top-ups).  Literal tables use the layout
 //               described there (also by the careful decoder of the same instantiation).
-enum : int { V_FAST = 1, V_PREFETCH = 4, V_STAGE = 16, V_CHAIN = 32 };
+//   V_PB2       the posState-indexed tables hold 4 positions instead of 16 (Lay<2>): chosen by the host for
+//               units whose pb is <= 2; not a tuning knob
+enum : int { V_FAST = 1, V_PREFETCH = 4, V_STAGE = 16, V_CHAIN = 32, V_PB2 = 64 };
+#define LZ_LAY(kV) Lay<((kV) & V_PB2) ? 2 : 4>
 constexpr uint32_t kF2Stage = 512;        // bytes of compressed input staged per refill (V_CHAIN)
 constexpr uint32_t kF2Margin = 41;        // a symbol consumes <= 21 bytes; the byte-ahead read adds 1
 constexpr uint32_t kF2MinInput = 128;     // do not (re)enter the V_CHAIN fast decoder with less input left
@@ -453,17 +465,17 @@ LZ_HD int rc_init(Dec &d) {
     do {                                                                            \
         uint16_t *lp_ = (LP);                                                       \
         uint32_t lb_, lv_;                                                          \
-        LZ_BIT(lp_ + LEN_CHOICE, lb_);                                              \
+        LZ_BIT(lp_ + Y::LEN_CHOICE, lb_);                                              \
         if (lb_ == 0) {                                                             \
-            LZ_TREE(lp_ + LEN_LOW + ((POS_STATE) << 3), 3, lv_, 0);                 \
+            LZ_TREE(lp_ + Y::LEN_LOW + ((POS_STATE) << 3), 3, lv_, 0);                 \
             (LEN) = lv_; (WHICH) = 0;                                               \
         } else {                                                                    \
-            LZ_BIT(lp_ + LEN_CHOICE2, lb_);                                         \
+            LZ_BIT(lp_ + Y::LEN_CHOICE2, lb_);                                         \
             if (LZ_LIKELY(lb_ == 0)) {                                              \
-                LZ_TREE(lp_ + LEN_MID + ((POS_STATE) << 3), 3, lv_, 0);             \
+                LZ_TREE(lp_ + Y::LEN_MID + ((POS_STATE) << 3), 3, lv_, 0);             \
                 (LEN) = 8 + lv_; (WHICH) = 1;                                       \
             } else {                                                                \
-                LZ_TREE(lp_ + LEN_HIGH, 8, lv_, 0x88);                              \
+                LZ_TREE(lp_ + Y::LEN_HIGH, 8, lv_, 0x88);                              \
                 (LEN) = 16 + lv_; (WHICH) = 2;                                      \
             }                                                                       \
         }                                                                           \
@@ -483,6 +495,7 @@ LZ_HD int rc_init(Dec &d) {
 // P: fixed tables (shared memory), L: literal tables (shared or global).
 template <int kV, bool kFast>
 LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, uint32_t &out_dist) {
+    using Y = LZ_LAY(kV);
     for (;;) {
         // fast decoder: leave when the margins are gone (at_end is then impossible);
         // careful decoder: hand over as soon as the fast one may run
@@ -497,9 +510,9 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
 
         LZ_FILL();
         const uint32_t pos_state = d.wpos & d.pos_mask;          // :22
-        const uint32_t state2 = (d.state << 4) + pos_state;      // :23
+        const uint32_t state2 = (d.state << Y::PB) + pos_state;      // :23
         uint32_t bit;
-        LZ_BIT(P + P_IS_MATCH + state2, bit);                    // :25-42
+        LZ_BIT(P + Y::IS_MATCH + state2, bit);                    // :25-42
 
         if (bit == 0) {  // literal, :44-175
             if (LZ_UNLIKELY(at_end)) {
@@ -563,16 +576,16 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
         }
 
         uint32_t len, which = 0, trunc_site;
-        uint16_t *rep4 = P + P_REP4 + (d.state << 2);
+        uint16_t *rep4 = P + Y::REP4 + (d.state << 2);
         LZ_BIT(rep4 + 0, bit);                                    // isRep, :195-213
         if (bit == 0) {  // simple match, :215-668
             d.rep3 = d.rep2; d.rep2 = d.rep1; d.rep1 = d.rep0;    // :216
             LZ_FILL();
-            LZ_LEN(P + P_LEN0, pos_state, len, which);            // :218-429
+            LZ_LEN(P + Y::LEN0, pos_state, len, which);            // :218-429
             d.state = d.state < 7 ? 7 : 10;                       // stateUpdateMatch, :431
             const uint32_t len_state = len > 3 ? 3 : len;         // :434-437
             uint32_t slot;
-            LZ_TREE(P + P_POS_SLOT + (len_state << 6), 6, slot, 0x21);  // :441-486, fills before bits 0, 5
+            LZ_TREE(P + Y::POS_SLOT + (len_state << 6), 6, slot, 0x21);  // :441-486, fills before bits 0, 5
             if (LZ_UNLIKELY(slot < 4)) {
                 d.rep0 = slot;                                    // :488-489
             } else {
@@ -580,7 +593,7 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
                 uint32_t dist = (2 | (slot & 1)) << nd, v;
                 if (LZ_UNLIKELY(slot < 14)) {                     // :494-546
                     // own sub-table layout: slot s starts at dist - 4; the reference's is dist - slot (:496)
-                    LZ_TREE_REV(P + P_POS_DEC + dist - 4, nd, v, 5);
+                    LZ_TREE_REV(P + Y::POS_DEC + dist - 4, nd, v, 5);
                     dist += v;
                 } else {                                          // :548-628
                     uint32_t res = 0;
@@ -627,7 +640,7 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
                     }
                     dist += res << 4;
                     LZ_FILL();
-                    LZ_TREE_REV(P + P_ALIGN, 4, v, 4);            // :580-625
+                    LZ_TREE_REV(P + Y::ALIGN, 4, v, 4);            // :580-625
                     dist += v;
                 }
                 d.rep0 = dist;
@@ -657,7 +670,7 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
             bool short_rep = false;
             LZ_BIT(rep4 + 1, bit);                                // isRepG0, :694-772
             if (bit == 0) {
-                LZ_BIT(P + P_IS_REP0_LONG + state2, bit);         // :715-755
+                LZ_BIT(P + Y::IS_REP0_LONG + state2, bit);         // :715-755
                 short_rep = (bit == 0);
             } else {
                 uint32_t dist;
@@ -676,7 +689,7 @@ LZ_HD uint32_t decode_run(Dec &d, uint16_t *P, uint16_t *L, uint32_t &out_len, u
                 trunc_site = 0;
             } else {
                 LZ_FILL();
-                LZ_LEN(P + P_LEN1, pos_state, len, which);        // :870-1101
+                LZ_LEN(P + Y::LEN1, pos_state, len, which);        // :870-1101
                 d.state = d.state < 7 ? 8 : 11;                   // stateUpdateRep
                 len += 2;
                 trunc_site = which == 0 ? 941 : (which == 1 ? 1035 : 1111);

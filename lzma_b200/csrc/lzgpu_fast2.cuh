@@ -178,7 +178,7 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
 
 // lenDecoder.Decode (len_decoder.go:34-60; live copies decompress.go:218-429, 870-1118).
 // SLEN (%5) = byte address of the coder, SLOW (%6) = byte address of its low tree for this posState
-// (mid tree = SLOW + 256, high tree = SLEN + 528).  Result 0..271.  The choice cells and the low
+// (mid tree = SLOW + MID, high tree = SLEN + HI: immediates that depend on the table layout, Lay<kPB>).  Result 0..271.  The choice cells and the low
 // tree's root and children are loaded by F2_LEN_LOADS, which the caller places as early as it can.
 #define F2_LEN_LOADS                                                                    \
     "ld.shared.u16 p, [%5];\n\t"                                                        \
@@ -186,7 +186,7 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
     "ld.shared.u16 pr0, [%6+2];\n\t"                                                    \
     "ld.shared.u16 lo, [%6+4];\n\t"                                                     \
     "ld.shared.u16 hi, [%6+6];\n\t"
-#define F2_LEN_BODY(L)                                                                  \
+#define F2_LEN_BODY(L, MID, HI)                                                                  \
     F2_CORE("p", "one") F2_UPD("p", "one")                                              \
     "st.shared.u16 [%5], pn;\n\t"                                                       \
     "@one bra.uni " L "CH2;\n\t"                                                        \
@@ -195,7 +195,7 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
     "mov.u32 %4, 0xfffffff8;\n\t"                                                       \
     "bra.uni " L "T3;\n\t"                                                              \
     L "CH2:\n\t"                                                                        \
-    "add.u32 bs, %6, 256;\n\t"                                                          \
+    "add.u32 bs, %6, " MID ";\n\t"                                                          \
     "ld.shared.u16 pr0, [bs+2];\n\t"                                                    \
     "ld.shared.u16 lo, [bs+4];\n\t"                                                     \
     "ld.shared.u16 hi, [bs+6];\n\t"                                                     \
@@ -213,7 +213,7 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
     "add.u32 %4, %4, t;\n\t"                                                            \
     "bra.uni " L "END;\n\t"                                                             \
     L "HI:\n\t"                                                                         \
-    "add.u32 bs, %5, 528;\n\t"                                                          \
+    "add.u32 bs, %5, " HI ";\n\t"                                                          \
     F2_ROOT("bs")                                                                       \
     F2_L0("bs", F2_LD) F2_L1(F2_LD) F2_L2(F2_LD) F2_L3(F2_LD) F2_L4(F2_LD) F2_L5(F2_LD) F2_L6(F2_LD) F2_L7(F2_NOLD) \
     "add.u32 t, ya, nS;\n\t"                                                            \
@@ -222,8 +222,8 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
     L "END:\n\t"
 #define F2_LEN(d, OUT, SLEN, SLOW)                                                      \
     asm volatile("{\n\t" F2_REGS ".reg .b32 bs, pc2, pr0;\n\t"                          \
-                 F2_LEN_LOADS F2_T0 F2_LEN_BODY("F2_LEN_") "}"                                \
-                 : F2_IO(d), "=&r"(OUT) : "r"(SLEN), "r"(SLOW) : "memory")
+                 F2_LEN_LOADS F2_T0 F2_LEN_BODY("F2_LEN_", "%7", "%8") "}"                    \
+                 : F2_IO(d), "=&r"(OUT) : "r"(SLEN), "r"(SLOW), "n"(2u * (Y::LEN_MID - Y::LEN_LOW)), "n"(2u * Y::LEN_HIGH) : "memory")
 // isRep (decompress.go:195-213; cell at AREP, value PREP loaded earlier) and, when it decodes 0, the
 // match length: the length coder's cells are in flight while isRep decodes.  OUT = 0xFFFFFFFF for a rep.
 #define F2_ISREP_LEN(d, OUT, SLEN, SLOW, AREP, PREP)                                    \
@@ -233,8 +233,9 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
                  "st.shared.u16 [%7], pn;\n\t"                                          \
                  "mov.u32 %4, 0xffffffff;\n\t"                                          \
                  "@one bra.uni F2_RL_END;\n\t"                                          \
-                 F2_LEN_BODY("F2_RL_") "}"                                              \
-                 : F2_IO(d), "=&r"(OUT) : "r"(SLEN), "r"(SLOW), "r"(AREP), "r"(PREP) : "memory")
+                 F2_LEN_BODY("F2_RL_", "%9", "%10") "}"                                 \
+                 : F2_IO(d), "=&r"(OUT) : "r"(SLEN), "r"(SLOW), "r"(AREP), "r"(PREP),                  \
+                   "n"(2u * (Y::LEN_MID - Y::LEN_LOW)), "n"(2u * Y::LEN_HIGH) : "memory")
 
 // ---- literal (decompress.go:49-169).  %5 = byte address S of the context's 0x300 cells,
 // %6 = 0x100 | match byte, %7 != 0: matched mode (state >= 7).  Result = the byte.
@@ -400,20 +401,21 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t 
     F2_U64P(uint8_t *, wc.pend_dst);
 #undef F2_U32
 #undef F2_U64P
+    using Y = LZ_LAY(kV);
     const uint32_t sP = d.sP;
     const uint32_t lane = LZ_LANE();
     // the next symbol's isMatch / isRep probabilities are loaded as soon as the current symbol has fixed
     // the state and the position they depend on (nothing in between touches those cells)
     uint32_t pos_state = d.wpos & d.pos_mask;                    // decompress.go:22
-    uint32_t a_im = sP + 2u * P_IS_MATCH + 2u * ((d.state << 4) + pos_state);   // :23
-    uint32_t a_rep = sP + 2u * P_REP4 + 8u * d.state;
+    uint32_t a_im = sP + 2u * Y::IS_MATCH + 2u * ((d.state << Y::PB) + pos_state);   // :23
+    uint32_t a_rep = sP + 2u * Y::REP4 + 8u * d.state;
     uint32_t p_im = f2_lds16(a_im);
     uint32_t p_rep = f2_lds16(a_rep);
 #define F2_NEXT_CTX()                                                                   \
     do {                                                                                \
         pos_state = d.wpos & d.pos_mask;                                                \
-        a_im = sP + 2u * P_IS_MATCH + 2u * ((d.state << 4) + pos_state);                \
-        a_rep = sP + 2u * P_REP4 + 8u * d.state;                                        \
+        a_im = sP + 2u * Y::IS_MATCH + 2u * ((d.state << Y::PB) + pos_state);                \
+        a_rep = sP + 2u * Y::REP4 + 8u * d.state;                                        \
         p_im = f2_lds16(a_im);                                                          \
         p_rep = f2_lds16(a_rep);                                                        \
     } while (0)
@@ -468,10 +470,10 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t 
         pl_valid = 0;
 
         uint32_t len;
-        const uint32_t state2 = (a_im - sP - 2u * P_IS_MATCH) >> 1;   // of THIS symbol (isRep0Long, :716)
+        const uint32_t state2 = (a_im - sP - 2u * Y::IS_MATCH) >> 1;   // of THIS symbol (isRep0Long, :716)
         const uint32_t a_rep_cur = a_rep, pos_state_cur = pos_state;
         // isRep (:195-213) and, for a simple match, its length (:218-429) in one block
-        F2_ISREP_LEN(d, len, sP + 2u * P_LEN0, sP + 2u * (P_LEN0 + LEN_LOW) + 16u * pos_state_cur, a_rep, p_rep);
+        F2_ISREP_LEN(d, len, sP + 2u * Y::LEN0, sP + 2u * (Y::LEN0 + Y::LEN_LOW) + 16u * pos_state_cur, a_rep, p_rep);
         if (LZ_LIKELY(len != 0xFFFFFFFFu)) {  // simple match, :215-668
             d.rep3 = d.rep2; d.rep2 = d.rep1; d.rep1 = d.rep0;    // :216
             d.state = d.state < 7 ? 7 : 10;                       // stateUpdateMatch, :431
@@ -484,7 +486,7 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t 
             if (LZ_UNLIKELY(d.wpos >= d.dict_size)) { d.wpos -= d.dict_size; d.full |= 2; }   // bit 1: became full by THIS match
             F2_NEXT_CTX();
             uint32_t slot;
-            F2_TREE6(d, slot, sP + 2u * P_POS_SLOT + (len_state << 7));   // :441-486
+            F2_TREE6(d, slot, sP + 2u * Y::POS_SLOT + (len_state << 7));   // :441-486
             slot -= 64;
             if (LZ_UNLIKELY(slot < 4)) {
                 d.rep0 = slot;                                    // :488-489
@@ -492,7 +494,7 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t 
                 const uint32_t nd = (slot >> 1) - 1;
                 uint32_t dist = (2 | (slot & 1)) << nd, v;
                 if (LZ_UNLIKELY(slot < 14)) {                     // :494-546, LSB first
-                    const uint32_t tb = sP + 2u * (P_POS_DEC + dist - 4);   // own sub-table layout (lzgpu_core.cuh)
+                    const uint32_t tb = sP + 2u * (Y::POS_DEC + dist - 4);   // own sub-table layout (lzgpu_core.cuh)
                     uint32_t m = 1;
                     v = 0;
 #pragma unroll 1
@@ -506,8 +508,8 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t 
                     dist += v;
                 } else {                                          // :548-628
                     // the align tree's root and its children: in flight during the direct bits
-                    const uint32_t al0 = f2_lds16(sP + 2u * P_ALIGN + 2), al2 = f2_lds16(sP + 2u * P_ALIGN + 4),
-                                   al3 = f2_lds16(sP + 2u * P_ALIGN + 6);
+                    const uint32_t al0 = f2_lds16(sP + 2u * Y::ALIGN + 2), al2 = f2_lds16(sP + 2u * Y::ALIGN + 4),
+                                   al3 = f2_lds16(sP + 2u * Y::ALIGN + 6);
                     // DecodeDirectBits (:549-576) normalises when the halved range drops below 2^24: first
                     // after g = 8 - clz(range) halvings, then after every 8th.  Between two normalisations
                     // step j compares against range >> j, so only `code` is carried (4 instructions a bit).
@@ -538,7 +540,7 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t 
                     }
                     dist += res << 4;
                     uint32_t m;
-                    F2_TREE4(d, m, sP + 2u * P_ALIGN, al0, al2, al3);   // :580-625
+                    F2_TREE4(d, m, sP + 2u * Y::ALIGN, al0, al2, al3);   // :580-625
                     dist += __brev(m) >> 28;
                 }
                 d.rep0 = dist;
@@ -569,7 +571,7 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t 
             uint32_t a = a_rep_cur + 2, pv = f2_lds16(a);
             F2_BIT(d, pv, a, bit);                                // isRepG0, :694-772
             if (bit == 0) {
-                a = sP + 2u * P_IS_REP0_LONG + 2u * state2;
+                a = sP + 2u * Y::IS_REP0_LONG + 2u * state2;
                 pv = f2_lds16(a);
                 F2_BIT(d, pv, a, bit);                            // :715-755
                 short_rep = (bit == 0);
@@ -592,7 +594,7 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t 
                 d.state = d.state < 7 ? 9 : 11;                   // stateUpdateShortRep
                 len = 1;
             } else {
-                F2_LEN(d, len, sP + 2u * P_LEN1, sP + 2u * (P_LEN1 + LEN_LOW) + 16u * pos_state_cur);   // :870-1101
+                F2_LEN(d, len, sP + 2u * Y::LEN1, sP + 2u * (Y::LEN1 + Y::LEN_LOW) + 16u * pos_state_cur);   // :870-1101
                 d.state = d.state < 7 ? 8 : 11;                   // stateUpdateRep
                 len += 2;
             }

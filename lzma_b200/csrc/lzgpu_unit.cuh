@@ -40,6 +40,9 @@
                  : "+r"(dst) : "l"(ptr), "r"((uint32_t)(cond)) : "memory")
 #define LZ_STAGE8(wc, off, dst)      /* copy stage (shared) */                          \
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(dst) : "r"((wc).s_stage + (off)) : "memory")
+#define LZ_STG128_IF(ptr, a, b, c, d, cond)   /* window (global), 16-byte aligned */    \
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.global.v4.u32 [%0], {%1, %2, %3, %4};\n\t}" \
+                 : : "l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d), "r"((uint32_t)(cond)) : "memory")
 #else
 #define LZ_STG8_IF(ptr, val, cond) do { if (cond) *(uint8_t *)(ptr) = (uint8_t)(val); } while (0)
 #define LZ_LDG8_IF(dst, ptr, cond) do { if (cond) (dst) = *(const uint8_t *)(ptr); } while (0)
@@ -98,6 +101,58 @@ LZ_DEV void wc_commit(WarpCopy &wc) {
     LZ_SYNC();
 }
 
+// Warp-cooperative copy of n bytes of compressed input (global, read-only) into the window (global), any
+// alignment on either side: an LZMA2 uncompressed chunk (uncompressedRead, reader2.go:252-294 -> window.ReadFrom,
+// window.go:142-155).  Bytes up to the first 16-byte boundary of dst and the last < 20 go one byte per lane; the
+// body is one 16-byte store per lane, its source taken as the five aligned 32-bit words that cover it and
+// funnel-shifted into place (consecutive chunks of a stream sit 3 header bytes apart, so source and destination
+// are rarely congruent).  Four vectors per lane are in flight per trip.  No word is loaded that does not lie
+// entirely inside [src rounded down to 4, src + n).
+LZ_DEV void warp_copy_in(uint8_t *dst, const uint8_t *src, uint32_t n) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t lane = LZ_LANE();
+    uint32_t head = (uint32_t)((16u - ((uint32_t)(uintptr_t)dst & 15u)) & 15u);
+    if (head > n) head = n;
+    {
+        uint32_t v = 0;
+        LZ_LDIN8_IF(v, src + (lane < head ? lane : 0u), lane < head);
+        LZ_STG8_IF(dst + lane, v, lane < head);
+    }
+    dst += head; src += head; n -= head;
+    const uint32_t a = (uint32_t)(uintptr_t)src & 3u, sh = 8u * a;
+    const uint8_t *s_al = src - a;
+    const uint32_t avail = n + a;                                       // bytes from s_al to the end of the source
+    const uint32_t nv = a ? (avail >= 4u ? (avail - 4u) >> 4 : 0u) : avail >> 4;   // vectors whose words lie inside
+    for (uint32_t j0 = 0; j0 < nv; j0 += 128) {                         // uniform trip count
+        uint32_t w[4][5];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t j = j0 + 32u * u + lane, live = j < nv;
+            const uint8_t *q = s_al + 16u * (live ? j : 0u);
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                w[u][k] = 0;
+                LZ_LD_IN32_IF(w[u][k], q + 4 * k, live && (k < 4 || a != 0u));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t j = j0 + 32u * u + lane, live = j < nv;
+            LZ_STG128_IF(dst + 16u * (live ? j : 0u), LZ_FUNNEL_R(w[u][0], w[u][1], sh), LZ_FUNNEL_R(w[u][1], w[u][2], sh),
+                         LZ_FUNNEL_R(w[u][2], w[u][3], sh), LZ_FUNNEL_R(w[u][3], w[u][4], sh), live);
+        }
+    }
+    const uint32_t done = 16u * nv, rest = n - done;                    // < 20 (a != 0) or < 16
+    {
+        uint32_t v = 0;
+        LZ_LDIN8_IF(v, src + done + (lane < rest ? lane : 0u), lane < rest);
+        LZ_STG8_IF(dst + done + lane, v, lane < rest);
+    }
+#else
+    memcpy(dst, src, n);
+#endif
+}
+
 LZ_DEV void probs_fill(uint16_t *p, uint32_t n) {  // initProbs, prob.go:3-7
 #if defined(__CUDA_ARCH__)
     // uniform trip count, predicated store that names its state space (tables live in shared memory, or in
@@ -118,8 +173,9 @@ LZ_DEV void probs_fill(uint16_t *p, uint32_t n) {  // initProbs, prob.go:3-7
 }
 
 // state.Reset (state.go:79-121): every table back to 1024, rep0..3 = 0, state = 0.
+template <int kV>
 LZ_DEV void coder_reset(Dec &d, uint16_t *P, uint16_t *L, uint32_t lit_bits) {
-    probs_fill(P, P_FIXED);
+    probs_fill(P, LZ_LAY(kV)::FIXED);
     probs_fill(L, 0x300u << lit_bits);
     d.rep0 = d.rep1 = d.rep2 = d.rep3 = 0;
     d.state = 0;
@@ -127,10 +183,11 @@ LZ_DEV void coder_reset(Dec &d, uint16_t *P, uint16_t *L, uint32_t lit_bits) {
 }
 
 // V_CHAIN addresses its tables and the input stage through 32-bit shared-window addresses
+template <int kV>
 LZ_DEV void set_shared_addrs(Dec &d, uint16_t *P, uint8_t *inbuf, uint8_t *stage) {
 #if defined(__CUDA_ARCH__)
     d.sP = (uint32_t)__cvta_generic_to_shared(P);
-    d.sL = d.sP + 2u * P_LIT;
+    d.sL = d.sP + 2u * LZ_LAY(kV)::LIT;
     d.sIn = (uint32_t)__cvta_generic_to_shared(inbuf);
     d.sStage = (uint32_t)__cvta_generic_to_shared(stage);
 #else
@@ -287,13 +344,24 @@ LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8
                 // This decoder does its common copies itself (lzgpu_fast2.cuh); what arrives here is rare
                 // (longer than 32 bytes, self-overlapping, or at the head / tail of a unit): copied at once,
                 // the context of a following literal read back from the window.
-                for (uint32_t b = 0; b < len; b += 32) {
-                    LZ_FOR_LANES(l) {
-                        const uint32_t i = b + l, live = i < len;
-                        uint32_t v = 0;
-                        LZ_LDG8_IF(v, src + (live ? (far ? i : src_index(i, dist)) : 0u), live);
-                        LZ_STG8_IF(dst + i, v, live);
+                // All loads, then all stores: every source byte predates the match (src_index < dist), so the up
+                // to nine bytes a lane moves (len <= 273) are in flight together -- one round trip to L2, not nine.
+                // An overlapping match repeats its first `dist` bytes: lane l's k-th byte is at (l + 32 k) mod dist,
+                // stepped without a division.
+                const uint32_t step = far ? 32u : 32u % dist;
+                LZ_FOR_LANES(l) {
+                    uint32_t si = far ? l : l % dist;
+                    uint32_t v[9];
+#pragma unroll
+                    for (uint32_t k = 0; k < 9; k++) {
+                        const uint32_t live = l + 32u * k < len;
+                        v[k] = 0;
+                        LZ_LDG8_IF(v[k], src + (live ? si : 0u), live);
+                        si += step;
+                        if (!far && si >= dist) si -= dist;
                     }
+#pragma unroll
+                    for (uint32_t k = 0; k < 9; k++) LZ_STG8_IF(dst + l + 32u * k, v[k], l + 32u * k < len);
                 }
                 LZ_SYNC();
                 d.prev_byte = dst[len - 1];
@@ -376,7 +444,7 @@ LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     wc.stage_sel = 0;
     wc.out_limit = io.out + io.out_cap;
     set_props(d, u.lc, u.lp, u.pb);
-    set_shared_addrs(d, P, io.inbuf, io.stage);
+    set_shared_addrs<kV>(d, P, io.inbuf, io.stage);
     wc.s_stage = d.sStage;
     d.prog = io.progress;
     d.out0 = io.out;
@@ -396,7 +464,7 @@ LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     d.in_end = io.in + io.in_len;
     d.status = LZGPU_OK;
     d.site = 0;
-    coder_reset(d, P, L, (uint32_t)u.lc + u.lp);
+    coder_reset<kV>(d, P, L, (uint32_t)u.lc + u.lp);
 
     int32_t r = 0;
     r = rc_init(d);
@@ -427,7 +495,7 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     wc.stage_sel = 0;
     wc.out_limit = io.out + io.out_cap;
     set_props(d, u.lc, u.lp, u.pb);
-    set_shared_addrs(d, P, io.inbuf, io.stage);
+    set_shared_addrs<kV>(d, P, io.inbuf, io.stage);
     wc.s_stage = d.sStage;
     d.prog = io.progress;
     d.out0 = io.out;
@@ -514,15 +582,7 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
             if (!short_payload) n = usz;
             if ((uint64_t)(out_limit - d.outp) < n) { status = LZGPU_OUTPUT_OVERFLOW; consumed = (uint64_t)(payload - io.in); break; }
             uint8_t *dst = d.outp;
-            for (uint64_t b = 0; b < n; b += 32) {
-                LZ_FOR_LANES(l) {
-                    const uint64_t i = b + l;
-                    const uint32_t live = i < n;
-                    uint32_t v = 0;
-                    LZ_LDIN8_IF(v, payload + (live ? i : 0), live);
-                    LZ_STG8_IF(dst + i, v, live);
-                }
-            }
+            warp_copy_in(dst, payload, (uint32_t)n);     // n <= 65 536
             LZ_SYNC();
             d.outp = dst + n;
             uint64_t wp = (uint64_t)d.wpos + n;      // window.ReadFrom, window.go:142-155
@@ -548,12 +608,14 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
             if (!have_coder || ctrl >= 0xC0) {      // DecodeProp(header[5]) + Renew (:158-165)
                 if (props >= 225) { status = LZGPU_INCORRECT_PROPERTIES; consumed = (uint64_t)(ip - io.in); break; }
                 const uint32_t lc = props % 9, r = props / 9, pb = r / 5, lp = r % 5;
-                if (lc + lp > lit_bits_cap) { status = LZGPU_RESULT_ERROR; site = LZGPU_SITE_LZMA2_PROPS; consumed = (uint64_t)(ip - io.in); break; }
+                if (lc + lp > lit_bits_cap || pb > LZ_LAY(kV)::PB) {   // tables of this launch too small: the unit lied
+                    status = LZGPU_RESULT_ERROR; site = LZGPU_SITE_LZMA2_PROPS; consumed = (uint64_t)(ip - io.in); break;
+                }
                 set_props(d, lc, lp, pb);
             }
             uint32_t lb = d.lc, m = d.lp_mask;
             while (m) { lb++; m >>= 1; }
-            coder_reset(d, P, L, lb);                // s.Reset() (:156-157) / newState
+            coder_reset<kV>(d, P, L, lb);                // s.Reset() (:156-157) / newState
             have_coder = 1;
         }
         const uint64_t in_rem = (uint64_t)(in_end - payload);

@@ -32,9 +32,13 @@ extern "C" int emu_decode_batch(const lzgpu_unit *units, int64_t n, const uint8_
             return LZGPU_E_INVALID;
         lzgpu_result r;
         bool alone = false;
+        if (u.kind == LZGPU_KIND_LZMA2_GROUP && !(u.flags & LZGPU_UF_BITS_KNOWN)) derive_lzma2_bits(in_base, u);
         if (!prepare_unit(u, r, &alone)) { results[i] = r; continue; }
         const uint32_t bits = u.lit_bits;
-        std::vector<uint16_t> probs((size_t)P_FIXED + ((size_t)0x300 << bits) + 64, 0xDEAD);
+        // same class choice as the device launch (lzgpu.cu, launch_decode): compact posState tables when pb <= 2
+        const bool pb2 = u.pos_bits <= 2;
+        const size_t fixed = pb2 ? Lay<2>::FIXED : Lay<4>::FIXED;
+        std::vector<uint16_t> probs(fixed + ((size_t)0x300 << bits) + 64, 0xDEAD);
         UnitIO io;
         io.in = in_base + u.in_off;
         io.in_len = u.in_len;
@@ -42,20 +46,19 @@ extern "C" int emu_decode_batch(const lzgpu_unit *units, int64_t n, const uint8_
         io.out_cap = u.out_cap;
         memset(&r, 0, sizeof r);
         r.status = LZGPU_NOT_RUN;
-        uint16_t *P = probs.data(), *L = probs.data() + P_LIT;
+        uint16_t *P = probs.data(), *L = probs.data() + fixed;
         alignas(16) uint8_t stage[128];
         io.stage = stage;
         alignas(16) uint8_t inbuf[kF2Stage];
         io.inbuf = inbuf;
         io.progress = nullptr;
+#define EMU_RUN(V) do { if (pb2) run_one<(V) | V_PB2>(u, io, P, L, bits, r); else run_one<(V)>(u, io, P, L, bits, r); } while (0)
         switch (variant) {
-            case 0: run_one<0>(u, io, P, L, bits, r); break;
-            case 5: run_one<5>(u, io, P, L, bits, r); break;
-            case 17: run_one<17>(u, io, P, L, bits, r); break;
-            case 21: run_one<21>(u, io, P, L, bits, r); break;
-            case 33: run_one<33>(u, io, P, L, bits, r); break;
-            default: run_one<1>(u, io, P, L, bits, r); break;
+            case 0: EMU_RUN(0); break;
+            case 33: EMU_RUN(33); break;
+            default: EMU_RUN(1); break;
         }
+#undef EMU_RUN
         if (alone) r.bytes_in += 13;
         r.device = -1;
         results[i] = r;
