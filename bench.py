@@ -44,7 +44,7 @@ STREAM_SIZE = 1 << 20
 METRIC = "decompressed GB/s (batch, device-timed)"
 # name of the dominant kernel as ncu prints it (variant 33 | V_PB2 = 97: the V_CHAIN decoder with compact posState
 # tables), and the tag profiles/traffic.json must carry for its dram-bytes figure to be quoted
-KERNEL_NAME = "lzgpu_decode_kernel<(bool)0, (int)97>(KArgs)"
+KERNEL_NAME = "void lzgpu_decode_kernel<0, 97>(KArgs)"
 KERNEL_TAG = "r02"
 
 

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblzgpu.so")
+LIB_PATH = os.environ.get("LZGPU_LIB") or os.path.join(_HERE, "liblzgpu.so")   # LZGPU_LIB: A/B builds of the same library (scripts/)
 
 # enum lzgpu_status
 OK, OK_INPUT_EXHAUSTED, RESULT_ERROR, INCORRECT_PROPERTIES, UNEXPECTED_EOF, OUTPUT_OVERFLOW = range(6)

@@ -44,8 +44,11 @@ struct KArgs {
 
 // One warp per CTA, one unit per warp.  Fixed tables (3.7 KB) always in shared
 // memory; literal tables in shared memory when lc+lp <= 4 (<= 24 KB), else in HBM.
+#ifndef LZGPU_MIN_CTAS
+#define LZGPU_MIN_CTAS 14   // 14 units of lc+lp = 3, pb <= 2 fit one SM's shared memory: the registers must allow as many
+#endif
 template <bool kLitGlobal, int kV>
-__global__ void __launch_bounds__(32, 14) lzgpu_decode_kernel(const KArgs a) {
+__global__ void __launch_bounds__(32, LZGPU_MIN_CTAS) lzgpu_decode_kernel(const KArgs a) {
     extern __shared__ __align__(16) uint16_t smem_probs[];
     const uint32_t slot = a.slot0 + blockIdx.x;
     const int32_t ui = a.order[slot];

@@ -137,6 +137,46 @@ def run_lzma2(ctx, n_blocks, size, distinct=32, steps=3):
                       "ms": round(ms, 2), "GBps": round(total / ms / 1e6, 3)}), flush=True)
 
 
+def run_uncompressed(ctx, n_units, size, steps=5):
+    """An LZMA2 batch made of uncompressed chunks only (what xz writes for incompressible data; the reference's own
+    benchmark of this path: reader2_test.go:31-36): every unit is a run of 64 KiB `0x01/0x02` chunks -- a copy, done by
+    the warp's 16-byte mover (lzgpu_unit.cuh warp_copy_in)."""
+    rng = np.random.default_rng(1)
+    data = rng.integers(0, 256, size, dtype=np.uint8).tobytes()
+    chunks = bytearray()
+    for pos in range(0, size, 1 << 16):
+        n = min(1 << 16, size - pos)
+        chunks += bytes([1 if pos == 0 else 2, (n - 1) >> 8, (n - 1) & 0xFF]) + data[pos:pos + n]
+    unit_stream = bytes(chunks)
+    stream = unit_stream * n_units + b"\0"
+    units, total, sst = B.scan_lzma2(stream, 8 << 20)
+    assert len(units) == n_units and total == n_units * size and sst == L.OK
+    in_buf = np.frombuffer(stream + bytes(16), dtype=np.uint8)
+    d_in = torch.from_numpy(in_buf.copy()).cuda()
+    d_out = torch.empty(total + 16, dtype=torch.uint8, device="cuda")
+    plan = ctx.plan(units, in_buf.nbytes, total + 16)
+    st = torch.cuda.current_stream().cuda_stream or 1
+    for _ in range(3):
+        plan.launch(d_in.data_ptr(), d_out.data_ptr(), st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        plan.launch(d_in.data_ptr(), d_out.data_ptr(), st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    res, _ = plan.results()
+    assert all(res[k].status == L.OK and res[k].bytes_out == size for k in range(n_units))
+    crc = plan.crc32(d_out.data_ptr())
+    assert (crc == zlib.crc32(data)).all()
+    plan.close()
+    del d_in, d_out
+    print(json.dumps({"kind": "lzma2-uncompressed-chunks", "units": n_units, "unit_bytes": size, "ms": round(ms, 3),
+                      "GBps": round(total / ms / 1e6, 1), "copy_GBps_read_plus_write": round(2 * total / ms / 1e6, 1),
+                      "verified": "device CRC-32 of every unit"}), flush=True)
+
+
 if __name__ == "__main__":
     with B.Context([0]) as ctx:
         if "--config5" in sys.argv:        # 16 384 x 4 MiB on one GPU (64 GiB of output in HBM)
@@ -150,10 +190,16 @@ if __name__ == "__main__":
             for n in (148, 1024):
                 run(ctx, "text", n, 1 << 20)
             sys.exit(0)
-        for n in (148, 592, 1024, 1924, 2048, 4096, 8192):
+        if "--uncompressed" in sys.argv:
+            run_uncompressed(ctx, 1024, 1 << 20)
+            run_uncompressed(ctx, 4096, 1 << 20)
+            sys.exit(0)
+        for n in (148, 592, 1024, 1924, 2048, 2072, 4096, 8192):
             run(ctx, "text", n, 1 << 20)
         run(ctx, "text", 2048, 4 << 20, distinct=16)      # BASELINE config 5's per-GPU shape at 8 GPUs
         run(ctx, "random", 148, 1 << 20)
         run(ctx, "random", 1024, 1 << 20)
         run(ctx, "mixed", 1024, 1 << 20)
         run_lzma2(ctx, 1024, 1 << 20)                     # BASELINE config 3: one 1 GiB LZMA2 stream
+        run_uncompressed(ctx, 1024, 1 << 20)
+        run_uncompressed(ctx, 4096, 1 << 20)
