@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define LZGPU_ABI_VERSION 1
+#define LZGPU_ABI_VERSION 2   /* 2: lzgpu_unit.pos_bits, LZGPU_UF_BITS_KNOWN / SUM_*, lzgpu_decode_batch_sums, CRC-64 */
 
 /* ---- per-unit outcome <-> reference error values (errors.go:5-12) ---- */
 enum lzgpu_status {
@@ -80,6 +80,9 @@ enum lzgpu_kind {
                                      chunk headers itself, so a binding that drops the two fields cannot make a
                                      unit fail; lzgpu_plan_create (input already on the device) takes lit_bits
                                      as given and assumes pos_bits = 4 */
+
+#define LZGPU_UF_SUM_CRC32 8u     /* lzgpu_decode_batch_sums: CRC-32 (zlib / .xz CHECK_CRC32) of this unit's decoded bytes */
+#define LZGPU_UF_SUM_CRC64 16u    /* lzgpu_decode_batch_sums: CRC-64/XZ (ECMA-182, .xz CHECK_CRC64) of them */
 
 typedef struct lzgpu_unit {
     uint64_t in_off, in_len;    /* compressed bytes: [in_off, in_off+in_len) of the batch input buffer */
@@ -178,6 +181,19 @@ int lzgpu_decode_batch(lzgpu_ctx *ctx, const lzgpu_unit *units, int64_t n_units,
                        uint8_t *out_base, uint64_t out_size,
                        lzgpu_result *results, lzgpu_stats *stats);
 
+/* lzgpu_decode_batch that also returns, for every unit flagged LZGPU_UF_SUM_CRC32 / _CRC64, that checksum of
+ * the bytes it decoded (sums[i]; a CRC-32 in the low 32 bits; 0 for units without a flag), computed on the GPU
+ * from the output where it lies while it travels back -- what an .xz reader needs to verify its blocks, or a
+ * caller of the reference would do with hash/crc32 / hash/crc64 over what Read returned, without a host pass
+ * over the payload.  A block made of several units: fold with lzgpu_crc32_combine / lzgpu_crc64_combine. */
+int lzgpu_decode_batch_sums(lzgpu_ctx *ctx, const lzgpu_unit *units, int64_t n_units,
+                            const uint8_t *in_base, uint64_t in_size,
+                            uint8_t *out_base, uint64_t out_size,
+                            lzgpu_result *results, lzgpu_stats *stats, uint64_t *sums);
+/* crc(A || B) from crc(A), crc(B) and the length of B (host arithmetic, O(log len_b)). */
+uint32_t lzgpu_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);
+uint64_t lzgpu_crc64_combine(uint64_t crc_a, uint64_t crc_b, uint64_t len_b);
+
 /* The same with DEVICE-resident buffers on context device `dev_index`, in three
  * steps so that a caller can keep the plan and time the launch alone:
  *   plan_create : validates, orders units longest-first, uploads descriptors
@@ -204,6 +220,8 @@ void lzgpu_free_pinned(void *p);
  * GPU after plan_launch on the same stream and returned in crc[n_units] (host memory).  Units that did not
  * run, or produced nothing, give 0.  Lets a batch too large to copy back be checked where it lies. */
 int lzgpu_plan_crc32(lzgpu_plan *plan, const uint8_t *d_out, uint32_t *crc);
+/* The same for CRC-64/XZ (ECMA-182 polynomial, reflected: the .xz CHECK_CRC64, xz's default check). */
+int lzgpu_plan_crc64(lzgpu_plan *plan, const uint8_t *d_out, uint64_t *crc);
 void lzgpu_plan_destroy(lzgpu_plan *plan);
 
 #ifdef __cplusplus

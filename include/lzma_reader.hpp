@@ -28,6 +28,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <future>
 #include <memory>
 #include <string>
 #include <tuple>
@@ -108,6 +109,24 @@ class Engine {
     // the batch entry point: all units in one lzgpu_decode_batch call (sharded over the engine's GPUs)
     std::pair<std::vector<Result>, error> DecodeBatch(const std::vector<Unit> &units, const uint8_t *in, size_t in_len,
                                                       uint8_t *out, size_t out_len);
+    // All folders (coders) of a 7z archive in ONE GPU call -- bodgit/sevenzip hands each folder to a registered
+    // decompressor separately (reader1.go:28-61, reader2.go:45-75), which is one reader and, here, one GPU call per
+    // folder; an archive reader that knows its folders up front decodes them together.  LZMA folders (props = 5
+    // bytes) become headerless LZMA1 units, LZMA2 folders (props = 1 byte) are cut at their dictionary resets.
+    // Property errors are the constructors' (ErrIncorrectProperties, errInsufficientProperties); decode errors are
+    // the readers' (ErrResultError, io::ErrUnexpectedEOF ...), with the bytes decoded before them.
+    struct Folder {
+        bool lzma2 = false;
+        std::vector<uint8_t> props;
+        uint64_t unpackSize = 0;      // LZMA: from the archive header; LZMA2: ignored (the chunk headers say)
+        const uint8_t *packed = nullptr;
+        size_t packedLen = 0;
+    };
+    struct FolderResult {
+        std::vector<uint8_t> out;
+        error err;
+    };
+    std::pair<std::vector<FolderResult>, error> DecodeFolders(const std::vector<Folder> &folders);
     int Devices() const;
     static error StatusError(int status);   // lzgpu_status -> the error value the reference returns
   private:
@@ -176,8 +195,10 @@ std::pair<std::unique_ptr<io::ReadCloser>, error> NewLZMADecompressorForSevenZip
 // ---- reader2.go ---------------------------------------------------------------------------------
 class Reader2 : public io::Reader {
   public:
+    ~Reader2();
     std::pair<int, error> Read(uint8_t *p, size_t len) override;
     size_t wave_bytes = 256u << 20;   // decoded bytes per GPU call (at least one unit)
+    bool decode_ahead = true;         // decode wave k+1 on a second thread while wave k is being served
 
   private:
     friend std::pair<std::unique_ptr<Reader2>, error> NewReader2(io::Reader &, int, std::shared_ptr<Engine>);
@@ -187,15 +208,21 @@ class Reader2 : public io::Reader {
     bool fill(size_t need);
     bool independentFrom(size_t pos);
     bool nextWave(std::vector<uint8_t> &wave);
-    void decodeWave();
+    struct Wave {
+        Bytes out;
+        error err;
+        bool last = false;
+    };
+    std::unique_ptr<Wave> decodeWave();   // reads the next wave's input and decodes it (runs on the ahead thread too)
+    void startAhead();
     io::Reader *in_ = nullptr;
     std::shared_ptr<Engine> eng_;
     uint32_t dict_ = 0;
-    std::vector<uint8_t> buf_;
-    Bytes out_;
+    std::vector<uint8_t> buf_;            // (touched only by whoever runs decodeWave: never two at a time)
     size_t rd_ = 0, pos_ = 0;
-    bool in_eof_ = false, last_ = false, decoded_ = false;
-    error err_;
+    bool in_eof_ = false;
+    std::unique_ptr<Wave> cur_;           // being served
+    std::future<std::unique_ptr<Wave>> next_;
 };
 
 std::pair<std::unique_ptr<Reader2>, error> NewReader2(io::Reader &inStream, int dictSize, std::shared_ptr<Engine> eng = nullptr);

@@ -21,7 +21,7 @@ E_OK, E_NO_DEVICE, E_CUDA, E_INVALID, E_NOMEM = 0, -1, -2, -3, -4
 # enum lzgpu_kind
 KIND_LZMA1_ALONE, KIND_LZMA1_RAW, KIND_LZMA2_GROUP = 0, 1, 2
 UNKNOWN_SIZE = (1 << 64) - 1
-UF_LZMA2_LAST, UF_LZMA2_FRESH, UF_BITS_KNOWN = 1, 2, 4
+UF_LZMA2_LAST, UF_LZMA2_FRESH, UF_BITS_KNOWN, UF_SUM_CRC32, UF_SUM_CRC64 = 1, 2, 4, 8, 16
 
 
 class Unit(C.Structure):
@@ -66,6 +66,10 @@ SYMBOLS = [
     ("lzgpu_plan_results", C.c_int, [_vp, C.POINTER(Result), C.POINTER(Stats)]),
     ("lzgpu_plan_launch_count", C.c_int, [_vp]),
     ("lzgpu_plan_crc32", C.c_int, [_vp, _u8p, C.POINTER(C.c_uint32)]),
+    ("lzgpu_plan_crc64", C.c_int, [_vp, _u8p, C.POINTER(C.c_uint64)]),
+    ("lzgpu_decode_batch_sums", C.c_int, [_vp, C.POINTER(Unit), _i64, _u8p, _u64, _u8p, _u64, C.POINTER(Result), C.POINTER(Stats), C.POINTER(C.c_uint64)]),
+    ("lzgpu_crc32_combine", C.c_uint32, [C.c_uint32, C.c_uint32, _u64]),
+    ("lzgpu_crc64_combine", C.c_uint64, [C.c_uint64, C.c_uint64, _u64]),
     ("lzgpu_alloc_pinned", C.c_void_p, [_u64]),
     ("lzgpu_free_pinned", None, [_vp]),
     ("lzgpu_plan_destroy", None, [_vp]),
@@ -95,7 +99,7 @@ def lib() -> C.CDLL:
             f = getattr(L, name)
             f.restype = res
             f.argtypes = args
-        if L.lzgpu_abi_version() != 1:
+        if L.lzgpu_abi_version() != 2:
             raise ImportError("liblzgpu.so ABI version mismatch")
         _lib = L
     return _lib

@@ -131,6 +131,17 @@ class Context:
         L.check(L.lib().lzgpu_decode_batch(self._h, arr, n, _ptr(in_buf), in_buf.nbytes, _ptr(out_buf), out_buf.nbytes, res, C.byref(st)))
         return res, st
 
+    def decode_batch_sums(self, units: Sequence[Unit], in_buf: np.ndarray, out_buf: np.ndarray):
+        """lzgpu_decode_batch_sums: as decode_batch, plus the CRC-32 / CRC-64 of every unit flagged UF_SUM_CRC32 /
+        UF_SUM_CRC64, computed on the GPU.  Returns (results, stats, sums[n] as numpy uint64)."""
+        n = len(units)
+        arr = units if isinstance(units, C.Array) else (Unit * max(n, 1))(*units)
+        res = (Result * max(n, 1))()
+        st = Stats()
+        sums = (C.c_uint64 * max(n, 1))()
+        L.check(L.lib().lzgpu_decode_batch_sums(self._h, arr, n, _ptr(in_buf), in_buf.nbytes, _ptr(out_buf), out_buf.nbytes, res, C.byref(st), sums))
+        return res, st, np.frombuffer(sums, dtype=np.uint64)[:n].copy()
+
     # ---- device buffers ----
     def plan(self, units: Sequence[Unit], in_size: int, out_size: int, dev_index: int = 0) -> "Plan":
         return Plan(self, units, in_size, out_size, dev_index)
@@ -164,6 +175,12 @@ class Plan:
         crc = (C.c_uint32 * max(self.n, 1))()
         L.check(L.lib().lzgpu_plan_crc32(self._h, d_out_ptr, crc))
         return np.frombuffer(crc, dtype=np.uint32)[:self.n].copy()
+
+    def crc64(self, d_out_ptr: int) -> np.ndarray:
+        """CRC-64/XZ of every unit's decoded bytes, computed on the device (lzgpu_plan_crc64)."""
+        crc = (C.c_uint64 * max(self.n, 1))()
+        L.check(L.lib().lzgpu_plan_crc64(self._h, d_out_ptr, crc))
+        return np.frombuffer(crc, dtype=np.uint64)[:self.n].copy()
 
     def close(self):
         if self._h:
@@ -241,7 +258,7 @@ def decode_alone_streams(ctx: Context, streams: Sequence[bytes], out_caps: Seque
     return results  # type: ignore[return-value]
 
 
-def decode_lzma2_stream(ctx: Context, data: bytes, dict_size: int = 0):
+def decode_lzma2_stream(ctx: Context, data: bytes, dict_size: int = 0, as_array: bool = False):
     """Decode one raw LZMA2 stream: scan into units, decode them in parallel,
     return (status, err_site, bytes).  The decoded bytes of units before the first
     failing one are returned with the failure, like the reference's reader would
@@ -251,9 +268,10 @@ def decode_lzma2_stream(ctx: Context, data: bytes, dict_size: int = 0):
     out_buf = _out_buffer(max(total, 16))
     res, _ = ctx.decode_batch(units, in_buf, out_buf)
     n_out = 0
+    fin = (lambda a: a) if as_array else (lambda a: a.tobytes())   # as_array: a view of the (possibly page-locked) buffer
     for u, r in zip(units, res):
         if r.status not in (L.OK,):
             n_out = u.out_off + r.bytes_out
-            return r.status, r.err_site, out_buf[:n_out].tobytes()
+            return r.status, r.err_site, fin(out_buf[:n_out])
         n_out = u.out_off + r.bytes_out
-    return L.OK, 0, out_buf[:n_out].tobytes()
+    return L.OK, 0, fin(out_buf[:n_out])

@@ -588,58 +588,77 @@ extern "C" void lzgpu_free_pinned(void *p) {
 // folded in a tree with  crc(A || B) = crc(A) * x^(8|B|) mod P  xor  crc(B)  (every right operand is full,
 // so step k multiplies by the one power x^(8 L 2^k)).
 namespace {
-constexpr uint32_t kCrcPoly = 0xEDB88320u;
-__host__ __device__ inline uint32_t crc_mulmod(uint32_t a, uint32_t b) {   // a * b mod P, reflected bit order
-    uint32_t m = 1u << 31, p = 0;
+// W = uint32_t: CRC-32 (IEEE 802.3, reflected 0xEDB88320: zlib's crc32, the .xz CHECK_CRC32);
+// W = uint64_t: CRC-64/XZ (ECMA-182, reflected 0xC96C5795D7870F42: the .xz CHECK_CRC64, xz's default).
+template <typename W> struct CrcP;
+template <> struct CrcP<uint32_t> { static constexpr uint32_t poly = 0xEDB88320u; };
+template <> struct CrcP<uint64_t> { static constexpr uint64_t poly = 0xC96C5795D7870F42ull; };
+
+template <typename W>
+__host__ __device__ inline W crc_mulmod(W a, W b) {   // a * b mod P, reflected bit order (bit 0 = highest power)
+    W m = (W)1 << (8 * sizeof(W) - 1), p = 0;
     for (;;) {
         if (a & m) { p ^= b; if ((a & (m - 1)) == 0) break; }
         m >>= 1;
-        b = (b & 1) ? (b >> 1) ^ kCrcPoly : b >> 1;
+        b = (b & 1) ? (b >> 1) ^ CrcP<W>::poly : b >> 1;
     }
     return p;
 }
-__host__ __device__ inline uint32_t crc_x_pow_8n(uint64_t n) {             // x^(8n) mod P
-    uint32_t sq = crc_mulmod(1u << 30, 1u << 30);   // x^2
-    sq = crc_mulmod(sq, sq);                        // x^4
-    sq = crc_mulmod(sq, sq);                        // x^8
-    uint32_t p = 1u << 31;                          // x^0
+template <typename W>
+__host__ __device__ inline W crc_x_pow_8n(uint64_t n) {             // x^(8n) mod P
+    const W x1 = (W)1 << (8 * sizeof(W) - 2);
+    W sq = crc_mulmod<W>(x1, x1);                   // x^2
+    sq = crc_mulmod<W>(sq, sq);                     // x^4
+    sq = crc_mulmod<W>(sq, sq);                     // x^8
+    W p = (W)1 << (8 * sizeof(W) - 1);              // x^0
     while (n) {
-        if (n & 1) p = crc_mulmod(sq, p);
-        sq = crc_mulmod(sq, sq);
+        if (n & 1) p = crc_mulmod<W>(sq, p);
+        sq = crc_mulmod<W>(sq, sq);
         n >>= 1;
     }
     return p;
 }
+// crc(A || B) from crc(A), crc(B) and |B|: the pre- and post-inversions cancel except for the terms below
+template <typename W>
+inline W crc_combine(W a, W b, uint64_t len_b) {
+    return len_b ? (W)(crc_mulmod<W>(crc_x_pow_8n<W>(len_b), a) ^ b) : a;
+}
 
-__global__ void __launch_bounds__(256) lzgpu_crc32_kernel(const lzgpu_unit *units, const lzgpu_result *results,
-                                                          const uint8_t *out_base, uint32_t *crc, int64_t n) {
-    __shared__ uint32_t T[4][256];
-    __shared__ uint32_t part[256];
-    __shared__ uint32_t powk[8];
+// One CTA per unit.  The unit's bytes are cut into 256 slices of equal length L, RIGHT-aligned (the leading slices may
+// be short or empty); each thread runs slicing-by-4 over its slice, then the 256 partial CRCs are folded in a tree with
+// crc(A || B) = crc(A) * x^(8|B|) mod P  xor  crc(B)  (every right operand is full, so step k multiplies by the one
+// power x^(8 L 2^k)).  `want`: only units whose flags have this bit are summed (0: all); the others' slots are left alone.
+template <typename W>
+__global__ void __launch_bounds__(256) lzgpu_crc_kernel(const lzgpu_unit *units, const lzgpu_result *results,
+                                                        const uint8_t *out_base, W *crc, int64_t n, uint32_t want) {
+    __shared__ W T[4][256];
+    __shared__ W part[256];
+    __shared__ W powk[8];
     const uint32_t t = threadIdx.x;
     {   // slicing tables: T[0] the byte table, T[j][b] = T[j-1][b] advanced by one zero byte
-        uint32_t c = t;
-        for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ kCrcPoly : c >> 1;
+        W c = t;
+        for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ CrcP<W>::poly : c >> 1;
         T[0][t] = c;
         __syncthreads();
         for (int j = 1; j < 4; j++) { c = (c >> 8) ^ T[0][c & 0xFF]; T[j][t] = c; }
         __syncthreads();   // every warp reads every entry
     }
     for (int64_t ui = blockIdx.x; ui < n; ui += gridDim.x) {
+        if (want && !(units[ui].flags & want)) continue;   // uniform over the CTA
         const uint64_t total = results[ui].status == LZGPU_NOT_RUN ? 0 : results[ui].bytes_out;
         const uint8_t *base = out_base + units[ui].out_off;
         const uint64_t L = ((total + 255) / 256 + 3) & ~(uint64_t)3;
         if (t == 0) {
-            uint32_t pw = crc_x_pow_8n(L);
-            for (int k = 0; k < 8; k++) { powk[k] = pw; pw = crc_mulmod(pw, pw); }
+            W pw = crc_x_pow_8n<W>(L);
+            for (int k = 0; k < 8; k++) { powk[k] = pw; pw = crc_mulmod<W>(pw, pw); }
         }
         // slice t = [total - (256 - t) L, total - (255 - t) L) clipped at 0
         const uint64_t back_hi = (uint64_t)(256 - t) * L, back_lo = (uint64_t)(255 - t) * L;
         const uint64_t lo = back_hi >= total ? 0 : total - back_hi, hi = back_lo >= total ? 0 : total - back_lo;
-        uint32_t c = 0;
+        W c = 0;
         if (hi > lo) {
             const uint8_t *p = base + lo, *e = base + hi;
-            c = 0xFFFFFFFFu;
+            c = ~(W)0;
             while (p < e && ((uintptr_t)p & 15)) c = (c >> 8) ^ T[0][(c ^ *p++) & 0xFF];
             for (; p + 16 <= e; p += 16) {
                 const uint4 w = *reinterpret_cast<const uint4 *>(p);
@@ -647,7 +666,10 @@ __global__ void __launch_bounds__(256) lzgpu_crc32_kernel(const lzgpu_unit *unit
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     c ^= ws[q];
-                    c = T[3][c & 0xFF] ^ T[2][(c >> 8) & 0xFF] ^ T[1][(c >> 16) & 0xFF] ^ T[0][c >> 24];
+                    const uint32_t l = (uint32_t)c;
+                    W nx = T[3][l & 0xFF] ^ T[2][(l >> 8) & 0xFF] ^ T[1][(l >> 16) & 0xFF] ^ T[0][l >> 24];
+                    if (sizeof(W) == 8) nx ^= (W)((uint64_t)c >> 32);
+                    c = nx;
                 }
             }
             while (p < e) c = (c >> 8) ^ T[0][(c ^ *p++) & 0xFF];
@@ -657,30 +679,37 @@ __global__ void __launch_bounds__(256) lzgpu_crc32_kernel(const lzgpu_unit *unit
         __syncthreads();
         for (int k = 0; k < 8; k++) {
             const uint32_t step = 1u << k;
-            if ((t & (2 * step - 1)) == 0) part[t] = crc_mulmod(powk[k], part[t]) ^ part[t + step];
+            if ((t & (2 * step - 1)) == 0) part[t] = crc_mulmod<W>(powk[k], part[t]) ^ part[t + step];
             __syncthreads();
         }
         if (t == 0) crc[ui] = part[0];
         __syncthreads();
     }
 }
-}  // namespace
 
-extern "C" int lzgpu_plan_crc32(lzgpu_plan *p, const uint8_t *d_out, uint32_t *crc) {
-    if (!p || !p->launched || (p->n > 0 && (!d_out || !crc))) return fail(LZGPU_E_INVALID, "plan_crc32: plan was not launched / null argument");
+// checksums of a launched plan's units into host memory; stream = the plan's
+template <typename W>
+int plan_crc(lzgpu_plan *p, const uint8_t *d_out, W *crc, const char *what) {
+    if (!p || !p->launched || (p->n > 0 && (!d_out || !crc))) return fail(LZGPU_E_INVALID, std::string(what) + ": plan was not launched / null argument");
     if (p->n == 0) return LZGPU_E_OK;
     DevState &ds = p->ctx->devs[p->dev_index];
     CUDA_TRY(cudaSetDevice(ds.device));
-    if (ensure(ds.d_sum, ds.sum_cap, sizeof(uint32_t) * (uint64_t)p->n)) return fail(LZGPU_E_NOMEM, "plan_crc32: cudaMalloc of the checksum array failed");
-    uint32_t *d_crc = reinterpret_cast<uint32_t *>(ds.d_sum);
+    if (ensure(ds.d_sum, ds.sum_cap, sizeof(W) * (uint64_t)p->n)) return fail(LZGPU_E_NOMEM, std::string(what) + ": cudaMalloc of the checksum array failed");
+    W *d_crc = reinterpret_cast<W *>(ds.d_sum);
     const unsigned grid = (unsigned)std::min<int64_t>(p->n, 148 * 16);
-    lzgpu_crc32_kernel<<<grid, 256, 0, p->last_stream>>>(p->d_units, p->d_results, d_out, d_crc, p->n);
+    lzgpu_crc_kernel<W><<<grid, 256, 0, p->last_stream>>>(p->d_units, p->d_results, d_out, d_crc, p->n, 0u);
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(crc, d_crc, sizeof(uint32_t) * (size_t)p->n, cudaMemcpyDeviceToHost, p->last_stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(crc, d_crc, sizeof(W) * (size_t)p->n, cudaMemcpyDeviceToHost, p->last_stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(p->last_stream);
-    if (e != cudaSuccess) return fail(LZGPU_E_CUDA, std::string("plan_crc32: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(LZGPU_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
     return LZGPU_E_OK;
 }
+}  // namespace
+
+extern "C" int lzgpu_plan_crc32(lzgpu_plan *p, const uint8_t *d_out, uint32_t *crc) { return plan_crc<uint32_t>(p, d_out, crc, "plan_crc32"); }
+extern "C" int lzgpu_plan_crc64(lzgpu_plan *p, const uint8_t *d_out, uint64_t *crc) { return plan_crc<uint64_t>(p, d_out, crc, "plan_crc64"); }
+extern "C" uint32_t lzgpu_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b) { return crc_combine<uint32_t>(crc_a, crc_b, len_b); }
+extern "C" uint64_t lzgpu_crc64_combine(uint64_t crc_a, uint64_t crc_b, uint64_t len_b) { return crc_combine<uint64_t>(crc_a, crc_b, len_b); }
 
 extern "C" int lzgpu_plan_results(lzgpu_plan *p, lzgpu_result *results, lzgpu_stats *stats) {
     if (!p || !p->launched) return fail(LZGPU_E_INVALID, "plan_results: plan was not launched");
@@ -724,7 +753,7 @@ struct Shard {
     int rc = 0;
     std::string err;
     double kernel_ms = 0, h2d_ms = 0, d2h_ms = 0;
-    int launches = 0;
+    int launches = 0, launches_extra = 0;
 };
 
 // Coalesce [off, off+len) ranges (sorted by off) into few large copies; returns the
@@ -792,7 +821,7 @@ __global__ void lzgpu_tail_copy_kernel(const uint64_t *desc, const uint8_t *src_
 }
 
 void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base, uint64_t in_size, uint8_t *out_base,
-               uint64_t out_size, lzgpu_result *results) {
+               uint64_t out_size, lzgpu_result *results, uint64_t *sums) {
     DevState &ds = ctx->devs[dev_index];
     // LZGPU_TRACE=1: host-side timeline of this shard on stderr (ms since the shard started)
     static const bool trace = getenv("LZGPU_TRACE") != nullptr;
@@ -940,8 +969,6 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
         }
         mark("kernel finished, tails enqueued");
         cudaEventRecord(e3, ds.copy_stream);
-        e = cudaStreamSynchronize(ds.copy_stream);
-        if (e != cudaSuccess && sh.rc == 0) cuda_fail(e, "D2H (streamed) sync");
     } else {
         if (sh.rc == 0) {
             // one copy per run of units that are adjacent in the caller's buffer and filled to their capacity
@@ -967,13 +994,46 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
         }
         cudaEventRecord(e3, ds.stream);
     }
+    if (sh.rc == 0 && sums) {
+        // checksums of the decoded bytes where they lie (LZGPU_UF_SUM_*): the units' CRCs are computed by the GPU
+        // while the tails / the output travel back on the copy stream -- no host pass over the payload
+        uint32_t any = 0;
+        for (size_t k = 0; k < n; k++) any |= sh.units[k].flags;
+        if (any & (LZGPU_UF_SUM_CRC32 | LZGPU_UF_SUM_CRC64)) {
+            const uint64_t need = (sizeof(uint64_t) + sizeof(uint32_t)) * (uint64_t)n;
+            if (ensure(ds.d_sum, ds.sum_cap, need)) { sh.rc = LZGPU_E_NOMEM; sh.err = "cudaMalloc of the checksum array failed"; }
+            else {
+                uint64_t *d64 = reinterpret_cast<uint64_t *>(ds.d_sum);
+                uint32_t *d32 = reinterpret_cast<uint32_t *>(ds.d_sum + sizeof(uint64_t) * n);
+                const unsigned grid = (unsigned)std::min<size_t>(n, 148 * 16);
+                if (any & LZGPU_UF_SUM_CRC32) lzgpu_crc_kernel<uint32_t><<<grid, 256, 0, ds.stream>>>(plan->d_units, plan->d_results, ds.d_out, d32, (int64_t)n, LZGPU_UF_SUM_CRC32);
+                if (any & LZGPU_UF_SUM_CRC64) lzgpu_crc_kernel<uint64_t><<<grid, 256, 0, ds.stream>>>(plan->d_units, plan->d_results, ds.d_out, d64, (int64_t)n, LZGPU_UF_SUM_CRC64);
+                std::vector<uint8_t> h(need);
+                e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), ds.d_sum, need, cudaMemcpyDeviceToHost, ds.stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(ds.stream);
+                if (e != cudaSuccess) cuda_fail(e, "checksum kernels");
+                else {
+                    const uint64_t *h64 = reinterpret_cast<const uint64_t *>(h.data());
+                    const uint32_t *h32 = reinterpret_cast<const uint32_t *>(h.data() + sizeof(uint64_t) * n);
+                    for (size_t k = 0; k < n; k++)
+                        sums[sh.idx[k]] = (sh.units[k].flags & LZGPU_UF_SUM_CRC64) ? h64[k] : (sh.units[k].flags & LZGPU_UF_SUM_CRC32) ? h32[k] : 0;
+                    sh.launches_extra = ((any & LZGPU_UF_SUM_CRC32) ? 1 : 0) + ((any & LZGPU_UF_SUM_CRC64) ? 1 : 0);
+                }
+            }
+        }
+    }
+    if (stream_out) {
+        e = cudaStreamSynchronize(ds.copy_stream);
+        if (e != cudaSuccess && sh.rc == 0) cuda_fail(e, "D2H (streamed) sync");
+    }
     e = cudaStreamSynchronize(ds.stream);
     if (e != cudaSuccess && sh.rc == 0) cuda_fail(e, "decode kernel / stream sync");
     mark("streams idle");
     if (sh.rc == 0) {
         for (size_t k = 0; k < n; k++) results[sh.idx[k]] = tmp[k];
         sh.kernel_ms = st.kernel_ms;
-        sh.launches = st.launches;
+        sh.launches = st.launches + sh.launches_extra;
         float a = 0, b = 0;
         cudaEventElapsedTime(&a, e0, e1);
         cudaEventElapsedTime(&b, e2, e3);
@@ -988,10 +1048,24 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
 
 }  // namespace
 
+static int decode_batch_impl(lzgpu_ctx *ctx, const lzgpu_unit *units, int64_t n, const uint8_t *in_base, uint64_t in_size,
+                             uint8_t *out_base, uint64_t out_size, lzgpu_result *results, lzgpu_stats *stats, uint64_t *sums);
 extern "C" int lzgpu_decode_batch(lzgpu_ctx *ctx, const lzgpu_unit *units, int64_t n,
                                   const uint8_t *in_base, uint64_t in_size,
                                   uint8_t *out_base, uint64_t out_size,
                                   lzgpu_result *results, lzgpu_stats *stats) {
+    return decode_batch_impl(ctx, units, n, in_base, in_size, out_base, out_size, results, stats, nullptr);
+}
+extern "C" int lzgpu_decode_batch_sums(lzgpu_ctx *ctx, const lzgpu_unit *units, int64_t n,
+                                       const uint8_t *in_base, uint64_t in_size,
+                                       uint8_t *out_base, uint64_t out_size,
+                                       lzgpu_result *results, lzgpu_stats *stats, uint64_t *sums) {
+    if (n > 0 && !sums) return fail(LZGPU_E_INVALID, "decode_batch_sums: null sums");
+    for (int64_t i = 0; i < n; i++) sums[i] = 0;
+    return decode_batch_impl(ctx, units, n, in_base, in_size, out_base, out_size, results, stats, sums);
+}
+static int decode_batch_impl(lzgpu_ctx *ctx, const lzgpu_unit *units, int64_t n, const uint8_t *in_base, uint64_t in_size,
+                             uint8_t *out_base, uint64_t out_size, lzgpu_result *results, lzgpu_stats *stats, uint64_t *sums) {
     if (!ctx || n < 0 || (n > 0 && (!units || !results))) return fail(LZGPU_E_INVALID, "decode_batch: bad arguments");
     if (ctx->devs.empty()) return fail(LZGPU_E_NO_DEVICE, "decode_batch: context has no device");
     std::lock_guard<std::mutex> lock(ctx->mu);
@@ -1024,11 +1098,11 @@ extern "C" int lzgpu_decode_batch(lzgpu_ctx *ctx, const lzgpu_unit *units, int64
         s.units.push_back(u);
     }
     if (nd == 1) {
-        run_shard(ctx, 0, shards[0], in_base, in_size, out_base, out_size, results);
+        run_shard(ctx, 0, shards[0], in_base, in_size, out_base, out_size, results, sums);
     } else {
         std::vector<std::thread> th;
         for (int d = 0; d < nd; d++)
-            th.emplace_back([&, d]() { run_shard(ctx, d, shards[(size_t)d], in_base, in_size, out_base, out_size, results); });
+            th.emplace_back([&, d]() { run_shard(ctx, d, shards[(size_t)d], in_base, in_size, out_base, out_size, results, sums); });
         for (auto &t : th) t.join();
     }
     lzgpu_stats st;

@@ -183,6 +183,102 @@ std::pair<std::vector<Result>, error> Engine::DecodeBatch(const std::vector<Unit
     return {std::move(res), nullptr};
 }
 
+std::pair<std::vector<Engine::FolderResult>, error> Engine::DecodeFolders(const std::vector<Folder> &folders) {
+    std::vector<FolderResult> res(folders.size());
+    struct Span { size_t first = 0, count = 0; uint64_t out_off = 0; bool lzma1 = false; uint64_t cap = 0; };
+    std::vector<Span> spans(folders.size());
+    std::vector<size_t> todo;
+    for (size_t i = 0; i < folders.size(); i++) {
+        const Folder &f = folders[i];
+        if (f.lzma2) {   // NewLZMA2DecompressorForSevenZip, reader2.go:49-75
+            if (f.props.size() != 1) { res[i].err = errInsufficientProperties; continue; }
+        } else {         // NewLZMADecompressorForSevenZip, reader1.go:32-61
+            if (f.props.size() < 5) { res[i].err = ErrIncorrectProperties; continue; }
+            if (std::get<3>(DecodeProp(f.props[0]))) { res[i].err = ErrIncorrectProperties; continue; }
+            // the size field of an archive header is untrusted: first capacity bounded by the packed size (as Reader1)
+            spans[i].cap = std::min<uint64_t>(f.unpackSize, std::max<uint64_t>(1 << 16, 8 * (uint64_t)f.packedLen));
+        }
+        todo.push_back(i);
+    }
+    static const uint8_t nothing[16] = {0};
+    while (!todo.empty()) {
+        // one input buffer (the folders' packed bytes, 16-byte aligned), one output buffer, one call
+        std::vector<Unit> units;
+        uint64_t in_size = 0, out_size = 0;
+        for (size_t i : todo) {
+            const Folder &f = folders[i];
+            Span &sp = spans[i];
+            sp.first = units.size();
+            sp.out_off = out_size;
+            if (f.lzma2) {
+                std::vector<Unit> us(16);
+                uint64_t total = 0;
+                int32_t sst = 0;
+                const uint8_t *pk = f.packed ? f.packed : nothing;
+                int64_t n = lzgpu_scan_lzma2(pk, f.packedLen, DecodeDictSize2(f.props[0]), us.data(), (int64_t)us.size(), &total, &sst);
+                if (n > (int64_t)us.size()) {
+                    us.resize((size_t)n);
+                    n = lzgpu_scan_lzma2(pk, f.packedLen, DecodeDictSize2(f.props[0]), us.data(), (int64_t)us.size(), &total, &sst);
+                }
+                for (int64_t k = 0; k < n; k++) {
+                    us[(size_t)k].in_off += in_size;
+                    us[(size_t)k].out_off += out_size;
+                    units.push_back(us[(size_t)k]);
+                }
+                sp.count = (size_t)std::max<int64_t>(n, 0);
+                out_size += (total + 15) & ~(uint64_t)15;
+            } else {
+                Unit u;
+                memset(&u, 0, sizeof u);
+                u.kind = LZGPU_KIND_LZMA1_RAW;
+                auto [lc, pb, lp, perr] = DecodeProp(f.props[0]);
+                (void)perr;
+                u.lc = lc; u.lp = lp; u.pb = pb;
+                u.dict_size = DecodeDictSize(f.props.data() + 1).first;
+                u.unpack_size = f.unpackSize;
+                u.in_off = in_size;
+                u.in_len = f.packedLen;
+                u.out_off = out_size;
+                u.out_cap = sp.cap;
+                units.push_back(u);
+                sp.count = 1;
+                sp.lzma1 = true;
+                out_size += (sp.cap + 15) & ~(uint64_t)15;
+            }
+            in_size += ((uint64_t)f.packedLen + 15) & ~(uint64_t)15;
+        }
+        Bytes in, out;
+        in.reset((size_t)in_size + 16);
+        out.reset((size_t)out_size + 16);
+        uint64_t off = 0;
+        for (size_t i : todo) {
+            if (folders[i].packedLen) memcpy(in.data() + off, folders[i].packed, folders[i].packedLen);
+            off += ((uint64_t)folders[i].packedLen + 15) & ~(uint64_t)15;
+        }
+        auto [r, err] = DecodeBatch(units, in.data(), in.size(), out.data(), out.size());
+        if (err) return {{}, err};
+        std::vector<size_t> again;
+        for (size_t i : todo) {
+            Span &sp = spans[i];
+            if (sp.lzma1 && r[sp.first].status == LZGPU_OUTPUT_OVERFLOW && sp.cap < folders[i].unpackSize) {
+                sp.cap = std::min<uint64_t>(sp.cap * 8, folders[i].unpackSize);   // the capacity guess was too small: this folder again
+                again.push_back(i);
+                continue;
+            }
+            uint64_t n_out = 0;
+            error e;
+            for (size_t k = sp.first; k < sp.first + sp.count; k++) {   // a folder's units are consecutive, and so are their outputs
+                n_out = units[k].out_off - sp.out_off + r[k].bytes_out;
+                if (r[k].status != LZGPU_OK) { e = StatusError(r[k].status); break; }
+            }
+            res[i].out.assign(out.data() + sp.out_off, out.data() + sp.out_off + n_out);
+            res[i].err = e;
+        }
+        todo.swap(again);
+    }
+    return {std::move(res), nullptr};
+}
+
 error Engine::StatusError(int status) {
     switch (status) {
     case LZGPU_OK:
@@ -424,19 +520,17 @@ bool Reader2::nextWave(std::vector<uint8_t> &wave) {
     }
 }
 
-void Reader2::decodeWave() {
-    decoded_ = true;
+std::unique_ptr<Reader2::Wave> Reader2::decodeWave() {
+    std::unique_ptr<Wave> w(new Wave());
     std::vector<uint8_t> wave;
     const bool last = nextWave(wave);
     if (rd_ > (8u << 20)) {   // drop what has been handed to the GPU
         buf_.erase(buf_.begin(), buf_.begin() + rd_);
         rd_ = 0;
     }
-    out_.clear();
-    pos_ = 0;
     if (!eng_) {
         auto [e, err] = Engine::Default();
-        if (err) { err_ = err; last_ = true; return; }
+        if (err) { w->err = err; w->last = true; return w; }
         eng_ = e;
     }
     std::vector<Unit> units(64);
@@ -447,11 +541,11 @@ void Reader2::decodeWave() {
         units.resize((size_t)n);
         n = lzgpu_scan_lzma2(wave.data(), wave.size(), dict_, units.data(), (int64_t)units.size(), &total, &sst);
     }
-    if (n < 0) { err_ = errors::New(std::string("lzgpu: ") + lzgpu_last_error()); last_ = true; return; }
+    if (n < 0) { w->err = errors::New(std::string("lzgpu: ") + lzgpu_last_error()); w->last = true; return w; }
     units.resize((size_t)n);
-    out_.reset((size_t)std::max<uint64_t>(total, 16));
-    auto [res, err] = eng_->DecodeBatch(units, wave.data(), wave.size(), out_.data(), out_.size());
-    if (err) { out_.clear(); err_ = err; last_ = true; return; }
+    w->out.reset((size_t)std::max<uint64_t>(total, 16));
+    auto [res, err] = eng_->DecodeBatch(units, wave.data(), wave.size(), w->out.data(), w->out.size());
+    if (err) { w->out.clear(); w->err = err; w->last = true; return w; }
     // the bytes of the units before the first failing one are delivered with the failure, as the reference's
     // reader would have delivered them
     uint64_t n_out = 0;
@@ -460,24 +554,43 @@ void Reader2::decodeWave() {
         n_out = units[k].out_off + res[k].bytes_out;
         if (res[k].status != LZGPU_OK) { status = res[k].status; break; }
     }
-    out_.truncate((size_t)n_out);
-    err_ = Engine::StatusError(status);
-    last_ = last || err_ != nullptr;
+    w->out.truncate((size_t)n_out);
+    w->err = Engine::StatusError(status);
+    w->last = last || w->err != nullptr;
+    return w;
+}
+
+// Wave k+1 is read and decoded on another thread while wave k is being served: a steady reader sees the GPU's
+// throughput rather than decode and delivery taking turns (the reference streams chunk by chunk, reader2.go:216-250;
+// here a Read would otherwise block for a whole wave).  Only that thread touches in_ / buf_ until its result is taken.
+void Reader2::startAhead() {
+    if (decode_ahead) next_ = std::async(std::launch::async, [this]() { return decodeWave(); });
+}
+
+Reader2::~Reader2() {
+    if (next_.valid()) next_.wait();
 }
 
 std::pair<int, error> Reader2::Read(uint8_t *p, size_t len) {   // reader2.go:216-250
-    if (!decoded_) decodeWave();
-    while (pos_ == out_.size() && !last_ && len) decodeWave();   // previous wave delivered: the next one
-    const size_t n = std::min(len, out_.size() - pos_);
+    if (!cur_) {
+        cur_ = decodeWave();
+        if (!cur_->last) startAhead();
+    }
+    while (pos_ == cur_->out.size() && !cur_->last && len) {   // previous wave delivered: the next one
+        cur_ = next_.valid() ? next_.get() : decodeWave();
+        pos_ = 0;
+        if (!cur_->last) startAhead();
+    }
+    const size_t n = std::min(len, cur_->out.size() - pos_);
     if (n) {
-        memcpy(p, out_.data() + pos_, n);
+        memcpy(p, cur_->out.data() + pos_, n);
         pos_ += n;
     }
     if (n == len && n > 0) return {(int)n, nullptr};
-    if (!last_) return {(int)n, nullptr};
-    if (err_) {
-        error e = err_;
-        err_ = nullptr;
+    if (!cur_->last) return {(int)n, nullptr};
+    if (cur_->err) {
+        error e = cur_->err;
+        cur_->err = nullptr;
         return {(int)n, e};
     }
     return {(int)n, io::EOF_};

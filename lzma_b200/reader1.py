@@ -106,14 +106,21 @@ class Reader1:
         u.unpack_size = self._unpack
         u.in_off, u.in_len = 0, len(payload)
         in_buf = np.frombuffer(payload, dtype=np.uint8) if payload else np.zeros(1, dtype=np.uint8)
-        cap = self._unpack if self._unpack != L.UNKNOWN_SIZE else max(1 << 16, 8 * len(payload))
+        # The header's size field is untrusted (13 bytes can claim 2^50): the first capacity is bounded by the
+        # payload and grows towards the declared size only when the decoder asks for more.  A retry decodes from the
+        # start again; as each attempt is 8x the previous one, all failed attempts together cost < 1/7 of the last.
+        known = self._unpack != L.UNKNOWN_SIZE
+        cap = max(1 << 16, 8 * len(payload))
+        if known:
+            cap = min(cap, max(self._unpack, 1))
         while True:
             u.out_off, u.out_cap = 0, cap
-            out = np.empty(max(cap, 16), dtype=np.uint8)
+            out = B._out_buffer(max(cap, 16))
             res, _ = ctx.decode_batch([u], in_buf, out)
             r = res[0]
-            if r.status == L.OUTPUT_OVERFLOW and self._unpack == L.UNKNOWN_SIZE and cap < (1 << 40):
-                cap *= 8          # the streaming reader has no capacity: grow and decode again
+            can_grow = cap < self._unpack if known else cap < (1 << 40)
+            if r.status == L.OUTPUT_OVERFLOW and can_grow:
+                cap = min(cap * 8, self._unpack) if known else cap * 8   # the streaming reader has no capacity: grow, decode again
                 continue
             break
         self._out = out[:r.bytes_out]

@@ -4,10 +4,14 @@ NewReader2 reads the first chunk header eagerly like the reference (reader2.go:2
 Read then works in WAVES: the input is read incrementally, chunk headers are
 walked on the host (reader2.go:100-214) until enough units -- chunk runs that begin at a dictionary
 reset -- are buffered (`wave_bytes` of decoded output), that wave is decoded in parallel on the
-GPU(s) and served; the next wave is read and decoded when the previous one has been delivered.
-Memory is bounded by the wave size (unless the stream never resets its dictionary), and a caller
-that stops reading early never pays for the rest of the stream."""
+GPU(s) and served; while a wave is being served the NEXT one is already being read and decoded on a
+second thread (decode-ahead: the library call releases the GIL), so a steady reader sees the GPU's
+throughput rather than decode and delivery taking turns.  Memory is bounded by two waves (unless the
+stream never resets its dictionary), and a caller that stops reading early pays for at most one
+wave beyond what it read."""
 from __future__ import annotations
+
+import threading
 
 import numpy as np
 
@@ -37,6 +41,8 @@ class Reader2:
         self._in_eof = False
         self._last = False
         self.wave_bytes = 256 << 20          # decoded bytes per GPU call (at least one unit)
+        self.decode_ahead = True             # decode wave k+1 on a second thread while wave k is served
+        self._ahead = None                   # (thread, result box) of the wave being decoded ahead
 
     def _initialize(self):
         """validateDictSize + startChunk (reader2.go:77-173) as far as the first header."""
@@ -131,6 +137,8 @@ class Reader2:
             first = False
 
     def _decode_wave(self):
+        """Reads the next wave's input and decodes it; returns (out, err, last).  Runs on the ahead thread too:
+        only one _decode_wave is ever in flight, and nothing else touches self._in / self._buf meanwhile."""
         if self._buf is None:                                   # first wave: header bytes read by NewReader2
             self._buf = bytearray(self._head)
             self._rd = 0
@@ -140,21 +148,51 @@ class Reader2:
             del self._buf[:self._rd]
             self._rd = 0
         ctx = self._ctx or default_context()
-        st, _site, out = B.decode_lzma2_stream(ctx, data, self._dict)
-        self._out = np.frombuffer(out, dtype=np.uint8)
+        st, _site, out = B.decode_lzma2_stream(ctx, data, self._dict, as_array=True)
+        err = _status_error(st)
+        return out, err, last or err is not None
+
+    def _start_ahead(self):
+        if not self.decode_ahead:
+            return
+        box = []
+
+        def run():
+            try:
+                box.append(self._decode_wave())
+            except BaseException as e:      # surfaces from the Read that needs this wave
+                box.append(e)
+        t = threading.Thread(target=run, daemon=True)
+        t.start()
+        self._ahead = (t, box)
+
+    def _take_wave(self):
+        if self._ahead is not None:
+            t, box = self._ahead
+            self._ahead = None
+            t.join()
+            if isinstance(box[0], BaseException):
+                raise box[0]
+            w = box[0]
+        else:
+            w = self._decode_wave()
+        self._out, self._err, self._last = w
         self._pos = 0
-        self._err = _status_error(st)
-        self._last = last or self._err is not None
+        if not self._last:
+            self._start_ahead()
 
     def Read(self, p) -> tuple:
         """reader2.go:216-250."""
         if self._out is None:
-            self._decode_wave()
+            self._take_wave()
         while self._pos == len(self._out) and not self._last and len(p):
-            self._decode_wave()                                 # previous wave delivered: next one
+            self._take_wave()                                   # previous wave delivered: the one decoded meanwhile
         n = min(len(p), len(self._out) - self._pos)
         if n:
-            p[:n] = self._out[self._pos:self._pos + n].tobytes()
+            if isinstance(p, np.ndarray):
+                p[:n] = self._out[self._pos:self._pos + n]
+            else:
+                p[:n] = self._out[self._pos:self._pos + n].tobytes()
             self._pos += n
         if n == len(p) and n > 0:
             return n, None

@@ -7,9 +7,10 @@ index at the end of the file says where each block starts and how large it decod
 blocks of a file, and all files of a batch, go to the GPU in ONE `lzgpu_decode_batch` call.
 
 Host side (this file): container parsing per the .xz file format 1.1.0 (stream header / footer,
-index, block headers, LZMA2 filter properties) and the integrity checks (CRC32 of the container
-fields; CRC32 / CRC64 / SHA-256 of each block's decoded bytes).  Device side: the same units and
-kernels as everything else (`lzgpu_scan_lzma2` cuts each block's payload at its dictionary resets).
+index, block headers, LZMA2 filter properties), the CRC32 of the container fields, and SHA-256 block
+checks.  Device side: the same units and kernels as everything else (`lzgpu_scan_lzma2` cuts each
+block's payload at its dictionary resets), and the CRC-32 / CRC-64 of each block's decoded bytes
+(`lzgpu_decode_batch_sums`: computed where the bytes lie, no host pass over the payload).
 Only the LZMA2 filter alone is supported (what `xz` writes by default); BCJ / delta chains are
 reported as unsupported.
 """
@@ -273,10 +274,24 @@ def build_units(files: list[bytes]):
 
 
 def decode_xz_files(ctx, files: list[bytes], verify: bool = True) -> list[bytes]:
-    """Decode a batch of .xz files: all blocks of all files in one `lzgpu_decode_batch` call."""
+    """Decode a batch of .xz files: all blocks of all files in one call.  CRC-32 / CRC-64 block checks are
+    computed by the GPU from the decoded bytes where they lie (lzgpu_decode_batch_sums: one checksum per
+    unit, folded per block with lzgpu_crc32_combine / lzgpu_crc64_combine); only SHA-256 blocks are hashed
+    on the host."""
     units, in_buf, out_size, per_file = build_units(files)
-    out_buf = np.empty(out_size, dtype=np.uint8)
-    res, _ = ctx.decode_batch(units, in_buf, out_buf)
+    out_buf = B._out_buffer(out_size)
+    if verify:
+        for _streams, _f_out, _n_out, blocks in per_file:
+            for b, first, cnt in blocks:
+                flag = {CHECK_CRC32: L.UF_SUM_CRC32, CHECK_CRC64: L.UF_SUM_CRC64}.get(b.check_type, 0)
+                for k in range(first, first + cnt):
+                    units[k].flags |= flag
+    if hasattr(ctx, "decode_batch_sums"):
+        res, _, sums = ctx.decode_batch_sums(units, in_buf, out_buf)
+    else:                                   # the lane emulation of the CPU test tier has no checksum kernels
+        res, _ = ctx.decode_batch(units, in_buf, out_buf)
+        sums = None
+    lib = L.lib()
     outs = []
     for fi, (streams, f_out, n_out, blocks) in enumerate(per_file):
         for b, first, cnt in blocks:
@@ -287,7 +302,19 @@ def decode_xz_files(ctx, files: list[bytes], verify: bool = True) -> list[bytes]
                 got += res[k].bytes_out
             if got != b.uncompressed_size:
                 raise XZError(f"file {fi}: block at {b.offset}: decoded {got} bytes, index says {b.uncompressed_size}")
-            if verify and not check_ok(b.check_type, b.check, out_buf[f_out + b.out_off:f_out + b.out_off + got]):
+            if not verify:
+                continue
+            if sums is not None and b.check_type in (CHECK_CRC32, CHECK_CRC64):
+                acc = 0
+                for k in range(first, first + cnt):
+                    if b.check_type == CHECK_CRC32:
+                        acc = lib.lzgpu_crc32_combine(acc, int(sums[k]) & 0xFFFFFFFF, res[k].bytes_out)
+                    else:
+                        acc = lib.lzgpu_crc64_combine(acc, int(sums[k]), res[k].bytes_out)
+                ok = acc == int.from_bytes(b.check, "little")
+            else:
+                ok = check_ok(b.check_type, b.check, out_buf[f_out + b.out_off:f_out + b.out_off + got])
+            if not ok:
                 raise XZError(f"file {fi}: block at {b.offset}: integrity check mismatch")
         outs.append(out_buf[f_out:f_out + n_out].tobytes())
     return outs

@@ -240,7 +240,17 @@ static void TestReader2WithFileVerification() {   // reader2_test.go:12-29
     r2->wave_bytes = 1;
     MD5 s2;
     auto [n2, e3] = io::Copy(s2, *r2);
-    REQUIRE(!e3 && n2 == n && s2.Sum() == randomFileMD5, "waves of one unit");
+    REQUIRE(!e3 && n2 == n && s2.Sum() == randomFileMD5, "waves of one unit (next wave decoded while this one is served)");
+    {
+        io::BytesReader in6(compressedData);
+        auto [r6, e9] = NewReader2(in6, 0);
+        REQUIRE(!e9, text(e9));
+        r6->wave_bytes = 1;
+        r6->decode_ahead = false;
+        MD5 s6;
+        auto [n6, e10] = io::Copy(s6, *r6);
+        REQUIRE(!e10 && n6 == n && s6.Sum() == randomFileMD5, "waves of one unit, no decode-ahead");
+    }
     // a long stream: the asset 40 times over (each copy starts with a dictionary reset -> 40 units in one wave,
     // 40 MiB of output: the reader's buffer is page-locked and the batch call streams into it)
     {
@@ -349,6 +359,56 @@ static void TestDecodeBatch() {   // the new batch entry point: many streams, on
     printf("ok   TestDecodeBatch (%zu units on %d device(s))\n", units.size(), eng->Devices());
 }
 
+static void TestDecodeFolders() {   // every folder of an archive in one GPU call (reader1.go:28-61, reader2.go:45-75)
+    auto [eng, err] = Engine::Default();
+    REQUIRE(!err, text(err));
+    const std::vector<uint8_t> a = ReadFile("a.lzma"), a2 = ReadFile("a_lp1_lc2_pb1.lzma"), rnd = ReadFile("randomfile.dat.lzma"),
+                               bad = ReadFile("bad_corrupted.lzma"), z = ReadFile("randomfile.dat.lzma2");
+    std::vector<Engine::Folder> folders;
+    std::vector<const char *> want;   // MD5 of the plaintext, "" = ErrResultError, "props" = constructor error
+    auto lzma1 = [&](const std::vector<uint8_t> &f, const char *md5) {
+        Engine::Folder fo;
+        fo.props.assign(f.begin(), f.begin() + 5);
+        fo.unpackSize = DecodeUnpackSize(f.data() + 5);
+        fo.packed = f.data() + 13;
+        fo.packedLen = f.size() - 13;
+        folders.push_back(fo);
+        want.push_back(md5);
+    };
+    for (int rep = 0; rep < 14; rep++) {
+        lzma1(a, aTxtMD5);
+        lzma1(a2, aTxtMD5);
+        lzma1(rnd, randomFileMD5);
+        lzma1(bad, "");
+        Engine::Folder f2;
+        f2.lzma2 = true;
+        f2.props = {0x16};
+        f2.packed = z.data();
+        f2.packedLen = z.size();
+        folders.push_back(f2);
+        want.push_back(randomFileMD5);
+    }
+    Engine::Folder p1;                       // errInsufficientProperties / ErrIncorrectProperties, like the constructors
+    p1.lzma2 = true;
+    folders.push_back(p1);
+    want.push_back("props2");
+    Engine::Folder p2;
+    p2.props = {225, 0, 0, 1, 0};
+    folders.push_back(p2);
+    want.push_back("props1");
+    auto [res, e2] = eng->DecodeFolders(folders);
+    REQUIRE(!e2 && res.size() == folders.size() && folders.size() >= 64, text(e2));
+    for (size_t i = 0; i < res.size(); i++) {
+        if (!strcmp(want[i], "props2")) { REQUIRE(res[i].err == errInsufficientProperties, text(res[i].err)); continue; }
+        if (!strcmp(want[i], "props1")) { REQUIRE(res[i].err == ErrIncorrectProperties, text(res[i].err)); continue; }
+        if (!want[i][0]) { REQUIRE(errors::Is(res[i].err, ErrResultError), text(res[i].err)); continue; }
+        MD5 sum;
+        sum.Write(res[i].out.data(), res[i].out.size());
+        REQUIRE(!res[i].err && sum.Sum() == want[i], "folder bytes");
+    }
+    printf("ok   TestDecodeFolders (%zu folders, one call)\n", folders.size());
+}
+
 int main(int argc, char **argv) {
     if (argc < 2) { fprintf(stderr, "usage: reader_test <assets dir> [--no-device]\n"); return 2; }
     dir = argv[1];
@@ -375,6 +435,7 @@ int main(int argc, char **argv) {
     TestReader2WithFileVerification();
     TestSevenZipAdapters();
     TestDecodeBatch();
+    TestDecodeFolders();
     printf("PASS %d checks\n", checks);
     return 0;
 }

@@ -25,7 +25,7 @@ def test_exports_every_declared_symbol():
     lib = L.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.lzgpu_abi_version() == 1
+    assert lib.lzgpu_abi_version() == 2
 
 
 def test_struct_layout():

@@ -148,6 +148,7 @@ def test_lzma2_reader_waves(ctx):
     src = _CountingIO(big)
     r, err = NewReader2(src, 1 << 20, ctx)
     r.wave_bytes = 1
+    r.decode_ahead = False                  # (with decode-ahead one more wave is read in the background)
     buf = bytearray(1000)
     assert r.Read(buf)[0] == 1000
     assert src.bytes_read < len(big) // 2
@@ -190,3 +191,87 @@ def test_sevenzip_adapters(ctx):
     n, err = lzma.io_copy(sink, rc)
     assert err is None and sink.getvalue() == d
     assert NewLZMA2DecompressorForSevenZip(b"", 0, [_Closer(l2)], ctx)[1] is E.errInsufficientProperties
+
+
+def test_decode_folders_one_call(ctx):
+    """all folders of an archive -- LZMA (headerless, props 5 bytes) and LZMA2 (props 1 byte, several
+    units each), a corrupt one, an untrusted size field, bad properties -- in ONE batch call; each folder's bytes
+    and error class equal the oracle's for the same folder read on its own."""
+    from lzma_b200.sevenzip import Folder, decode_folders
+    from oracle import oracle as O
+    folders, want = [], []
+    for i in range(40):
+        lc, lp, pb = [(3, 0, 2), (0, 2, 0), (4, 0, 4), (1, 1, 1)][i % 4]
+        d = (K.text_block, K.mixed_block)[i % 2](4000 + i, 30_000 + 1777 * i)
+        s = K.compress_alone(d, lc, lp, pb, 1 << 18, preset=1 + i % 6)
+        folders.append(Folder(False, s[:5], len(d), s[13:]))
+        want.append((d, None))
+    for i in range(24):
+        blocks = [K.text_block(4100 + 3 * i + j, 40_000 + 999 * j) if (i + j) % 3 else K.random_block(4100 + i + j, 70_000) for j in range(3)]
+        s = K.lzma2_with_resets(blocks, dict_size=1 << 20, preset=1 + i % 4)
+        folders.append(Folder(True, bytes([0x10]), 0, s))        # 0x10 = 1 MiB
+        want.append((b"".join(blocks), None))
+    bad = cases.asset("bad_corrupted.lzma")
+    folders.append(Folder(False, bad[:5], DecodeUnpackSize(bad[5:13]), bad[13:]))
+    want.append((None, E.ErrResultError))
+    a = cases.asset("a.lzma")
+    folders.append(Folder(False, a[:5], 1 << 50, a[13:]))        # a header that claims 2^50 bytes must not allocate them
+    want.append((None, "any"))
+    folders.append(Folder(True, b"", 0, b"\0"))
+    want.append((b"", E.errInsufficientProperties))
+    folders.append(Folder(False, bytes([225, 0, 0, 1, 0]), 10, b"\0" * 10))
+    want.append((b"", E.ErrIncorrectProperties))
+    trunc = K.lzma2_with_resets([K.text_block(4300, 90_000)], dict_size=1 << 20)
+    folders.append(Folder(True, bytes([0x10]), 0, trunc[:len(trunc) // 2]))
+    want.append((None, E.ErrUnexpectedEOF))
+    assert len(folders) >= 64
+    got = decode_folders(ctx, folders)
+    for i, ((data, err), (wd, we)) in enumerate(zip(got, want)):
+        if we is None:
+            assert err is None and data == wd, i
+        elif we == "any":
+            r = O.lzma_raw(folders[i].packed, 3, 0, 2, 1 << 23, 1 << 50, 1 << 20)
+            assert (err is None) == (r.status in (O.OK, O.OK_INPUT_EXHAUSTED)) and data == r.data, i
+        else:
+            assert E.Is(err, we), (i, err)
+    # folder by folder through the sevenzip constructors: the same bytes
+    for i in (0, 41, 45):
+        f = folders[i]
+        ctor = NewLZMA2DecompressorForSevenZip if f.lzma2 else NewLZMADecompressorForSevenZip
+        rc, err = ctor(f.props, f.unpack_size, [io.BytesIO(f.packed)], ctx)
+        assert err is None
+        sink = io.BytesIO()
+        _, err = lzma.io_copy(sink, rc)
+        assert err is None and sink.getvalue() == got[i][0]
+
+
+def test_lzma2_reader_decode_ahead(ctx):
+    """N1: while a wave is served the next one is decoded on a second thread; small and large reads, waves of one
+    unit, a failing unit in a later wave, and a caller that stops early (the ahead thread must not be left hanging)."""
+    blocks = [K.text_block(4400 + i, 60_000 + 4321 * i) for i in range(9)]
+    stream = K.lzma2_with_resets(blocks, dict_size=1 << 20)
+    plain = b"".join(blocks)
+    for ahead in (True, False):
+        for wave, bufsize in ((1, 7_000), (150_000, 1 << 20), (1 << 30, 32 * 1024)):
+            r, err = NewReader2(io.BytesIO(stream), 1 << 20, ctx)
+            assert err is None
+            r.wave_bytes, r.decode_ahead = wave, ahead
+            sink = io.BytesIO()
+            _, err = lzma.io_copy(sink, r, bufsize)
+            assert err is None and sink.getvalue() == plain, (ahead, wave)
+    # corruption inside the 6th unit: the bytes before it are delivered, then ErrResultError
+    units, _, _ = lzma.scan_lzma2(stream, 1 << 20)
+    bad = bytearray(stream)
+    bad[units[5].in_off + units[5].in_len // 2] ^= 0x40
+    r, err = NewReader2(io.BytesIO(bytes(bad)), 1 << 20, ctx)
+    r.wave_bytes = 1
+    sink = io.BytesIO()
+    _, err = lzma.io_copy(sink, r, 10_000)
+    assert err is not None and sink.getvalue()[:units[5].out_off] == plain[:units[5].out_off]
+    # stop after the first bytes
+    r, err = NewReader2(io.BytesIO(stream), 1 << 20, ctx)
+    r.wave_bytes = 1
+    buf = bytearray(100)
+    n, err = r.Read(buf)
+    assert n == 100 and err is None and bytes(buf) == plain[:100]
+    del r
