@@ -125,7 +125,7 @@ type wave struct {
 	last bool
 }
 
-const defaultWaveBytes = 256 << 20
+const defaultWaveBytes = 1 << 30 // a wave takes as long as its longest unit (~100 ms per MiB of text): large waves give throughput
 
 // fill makes at least need bytes available in r.buf[from:]; false if the input ended first.
 func (r *gpuReader2) fill(from, need int) bool {

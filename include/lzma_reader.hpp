@@ -197,7 +197,7 @@ class Reader2 : public io::Reader {
   public:
     ~Reader2();
     std::pair<int, error> Read(uint8_t *p, size_t len) override;
-    size_t wave_bytes = 256u << 20;   // decoded bytes per GPU call (at least one unit)
+    size_t wave_bytes = (size_t)1 << 30;   // decoded bytes per GPU call (at least one unit).  A wave takes as long as its longest unit (~100 ms per MiB of text), however many units it has: large waves are what gives throughput
     bool decode_ahead = true;         // decode wave k+1 on a second thread while wave k is being served
 
   private:
@@ -222,6 +222,7 @@ class Reader2 : public io::Reader {
     size_t rd_ = 0, pos_ = 0;
     bool in_eof_ = false;
     std::unique_ptr<Wave> cur_;           // being served
+    std::unique_ptr<Wave> spare_;         // delivered: its buffer goes to the next decodeWave
     std::future<std::unique_ptr<Wave>> next_;
 };
 

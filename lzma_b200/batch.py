@@ -7,6 +7,7 @@ per-unit ``lzgpu_result``s.  All decoding happens in liblzgpu.so on the GPU.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass
 from typing import Iterable, Sequence
 
@@ -91,6 +92,7 @@ class Context:
 
     def __init__(self, devices: Iterable[int] | None = None):
         lib = L.lib()
+        self._lock = threading.Lock()     # one call at a time per context; close() waits for a call in flight on another thread
         self._h = C.c_void_p()
         if devices is None:
             rc = lib.lzgpu_ctx_create(None, 0, C.byref(self._h))
@@ -105,9 +107,15 @@ class Context:
         return L.lib().lzgpu_ctx_device_count(self._h)
 
     def close(self):
-        if self._h:
-            L.lib().lzgpu_ctx_destroy(self._h)
-            self._h = C.c_void_p()
+        with self._lock:
+            if self._h:
+                L.lib().lzgpu_ctx_destroy(self._h)
+                self._h = C.c_void_p()
+
+    def _handle(self):
+        if not self._h:
+            raise L.LzgpuError(L.E_INVALID, "the context has been closed")
+        return self._h
 
     def __enter__(self):
         return self
@@ -128,7 +136,8 @@ class Context:
         arr = units if isinstance(units, C.Array) else (Unit * max(n, 1))(*units)
         res = (Result * max(n, 1))()
         st = Stats()
-        L.check(L.lib().lzgpu_decode_batch(self._h, arr, n, _ptr(in_buf), in_buf.nbytes, _ptr(out_buf), out_buf.nbytes, res, C.byref(st)))
+        with self._lock:
+            L.check(L.lib().lzgpu_decode_batch(self._handle(), arr, n, _ptr(in_buf), in_buf.nbytes, _ptr(out_buf), out_buf.nbytes, res, C.byref(st)))
         return res, st
 
     def decode_batch_sums(self, units: Sequence[Unit], in_buf: np.ndarray, out_buf: np.ndarray):
@@ -139,7 +148,8 @@ class Context:
         res = (Result * max(n, 1))()
         st = Stats()
         sums = (C.c_uint64 * max(n, 1))()
-        L.check(L.lib().lzgpu_decode_batch_sums(self._h, arr, n, _ptr(in_buf), in_buf.nbytes, _ptr(out_buf), out_buf.nbytes, res, C.byref(st), sums))
+        with self._lock:
+            L.check(L.lib().lzgpu_decode_batch_sums(self._handle(), arr, n, _ptr(in_buf), in_buf.nbytes, _ptr(out_buf), out_buf.nbytes, res, C.byref(st), sums))
         return res, st, np.frombuffer(sums, dtype=np.uint64)[:n].copy()
 
     # ---- device buffers ----
@@ -258,14 +268,14 @@ def decode_alone_streams(ctx: Context, streams: Sequence[bytes], out_caps: Seque
     return results  # type: ignore[return-value]
 
 
-def decode_lzma2_stream(ctx: Context, data: bytes, dict_size: int = 0, as_array: bool = False):
+def decode_lzma2_stream(ctx: Context, data: bytes, dict_size: int = 0, as_array: bool = False, out_pool=None):
     """Decode one raw LZMA2 stream: scan into units, decode them in parallel,
     return (status, err_site, bytes).  The decoded bytes of units before the first
     failing one are returned with the failure, like the reference's reader would
     have delivered them."""
     units, total, sst = scan_lzma2(data, dict_size)
     in_buf = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(1, dtype=np.uint8)
-    out_buf = _out_buffer(max(total, 16))
+    out_buf = out_pool(max(total, 16)) if out_pool else _out_buffer(max(total, 16))   # out_pool: the caller recycles (page-locked) buffers
     res, _ = ctx.decode_batch(units, in_buf, out_buf)
     n_out = 0
     fin = (lambda a: a) if as_array else (lambda a: a.tobytes())   # as_array: a view of the (possibly page-locked) buffer

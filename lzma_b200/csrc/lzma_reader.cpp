@@ -521,7 +521,11 @@ bool Reader2::nextWave(std::vector<uint8_t> &wave) {
 }
 
 std::unique_ptr<Reader2::Wave> Reader2::decodeWave() {
-    std::unique_ptr<Wave> w(new Wave());
+    // a delivered wave's buffer is reused (page-locked memory is dear to allocate): three rotate -- served, decoding, spare
+    std::unique_ptr<Wave> w = std::move(spare_);
+    if (!w) w.reset(new Wave());
+    w->err = nullptr;
+    w->last = false;
     std::vector<uint8_t> wave;
     const bool last = nextWave(wave);
     if (rd_ > (8u << 20)) {   // drop what has been handed to the GPU
@@ -577,7 +581,9 @@ std::pair<int, error> Reader2::Read(uint8_t *p, size_t len) {   // reader2.go:21
         if (!cur_->last) startAhead();
     }
     while (pos_ == cur_->out.size() && !cur_->last && len) {   // previous wave delivered: the next one
+        std::unique_ptr<Wave> done = std::move(cur_);
         cur_ = next_.valid() ? next_.get() : decodeWave();
+        spare_ = std::move(done);                              // (no decodeWave is running here: the ahead thread has finished)
         pos_ = 0;
         if (!cur_->last) startAhead();
     }

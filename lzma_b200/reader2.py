@@ -40,9 +40,11 @@ class Reader2:
         self._rd = 0
         self._in_eof = False
         self._last = False
-        self.wave_bytes = 256 << 20          # decoded bytes per GPU call (at least one unit)
+        self.wave_bytes = 1 << 30            # decoded bytes per GPU call (at least one unit): a wave takes as long as its longest unit, so large waves are what gives throughput
         self.decode_ahead = True             # decode wave k+1 on a second thread while wave k is served
         self._ahead = None                   # (thread, result box) of the wave being decoded ahead
+        self._pool = []                      # output buffers of delivered waves (page-locked memory is dear to allocate)
+        self._cur_buf = None
 
     def _initialize(self):
         """validateDictSize + startChunk (reader2.go:77-173) as far as the first header."""
@@ -148,9 +150,28 @@ class Reader2:
             del self._buf[:self._rd]
             self._rd = 0
         ctx = self._ctx or default_context()
-        st, _site, out = B.decode_lzma2_stream(ctx, data, self._dict, as_array=True)
+        held = []
+
+        def pool(n):
+            held.append(self._buffer(n))
+            return held[0]
+        st, _site, out = B.decode_lzma2_stream(ctx, data, self._dict, as_array=True, out_pool=pool)
         err = _status_error(st)
-        return out, err, last or err is not None
+        return out, err, last or err is not None, (held[0] if held else None)
+
+    def _buffer(self, n: int):
+        """An output buffer of at least n bytes: a delivered wave's if one fits (three rotate: served, decoding, spare)."""
+        for k, b in enumerate(self._pool):
+            if b.nbytes >= n:
+                return self._pool.pop(k)
+        self._pool.clear()
+        return B._out_buffer(n)
+
+    def close(self):
+        """Waits for a wave being decoded ahead (call before closing the context the reader uses)."""
+        if self._ahead is not None:
+            self._ahead[0].join()
+            self._ahead = None
 
     def _start_ahead(self):
         if not self.decode_ahead:
@@ -176,7 +197,9 @@ class Reader2:
             w = box[0]
         else:
             w = self._decode_wave()
-        self._out, self._err, self._last = w
+        if self._cur_buf is not None:
+            self._pool.append(self._cur_buf)                   # the delivered wave's buffer: reuse it
+        self._out, self._err, self._last, self._cur_buf = w
         self._pos = 0
         if not self._last:
             self._start_ahead()

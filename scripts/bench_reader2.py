@@ -29,8 +29,8 @@ with open(path, "wb") as f:
         f.write(blob[offs[k]:offs[k] + lens[k]].tobytes())
     f.write(b"\0")
 exe = os.path.join(ROOT, "tests", "cpp", "_build", "reader2_bench")
-for bufsize in (32 << 10, 1 << 20):
-    print(subprocess.run([exe, path, str(bufsize)], capture_output=True, text=True).stdout.strip(), flush=True)
+for bufsize, wave in ((32 << 10, 1 << 30), (1 << 20, 1 << 30), (1 << 20, 2 << 30), (1 << 20, 256 << 20)):
+    print(subprocess.run([exe, path, str(bufsize), str(wave)], capture_output=True, text=True).stdout.strip(), flush=True)
 
 import io  # noqa: E402
 from lzma_b200.reader2 import NewReader2  # noqa: E402

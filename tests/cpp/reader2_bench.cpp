@@ -43,7 +43,7 @@ int main(int argc, char **argv) {
     if (!f) { perror(argv[1]); return 2; }
     std::vector<uint8_t> stream((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
     const size_t bufsize = argc > 2 ? strtoull(argv[2], nullptr, 0) : (1u << 20);
-    const size_t wave = argc > 3 ? strtoull(argv[3], nullptr, 0) : (256u << 20);
+    const size_t wave = argc > 3 ? strtoull(argv[3], nullptr, 0) : ((size_t)1 << 30);
     uint64_t n = 0;
     uint32_t s = 0;
     run(stream, bufsize, wave, true, &n, &s);                       // warm-up: context, slabs, page-locked buffers
