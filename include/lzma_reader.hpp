@@ -28,8 +28,9 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
-#include <future>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <tuple>
 #include <utility>
@@ -141,6 +142,15 @@ class Bytes {
     Bytes() = default;
     Bytes(const Bytes &) = delete;
     Bytes &operator=(const Bytes &) = delete;
+    Bytes(Bytes &&o) noexcept : p_(o.p_), size_(o.size_), cap_(o.cap_), pinned_(o.pinned_) { o.p_ = nullptr; o.size_ = o.cap_ = 0; o.pinned_ = false; }
+    Bytes &operator=(Bytes &&o) noexcept {
+        if (this != &o) {
+            release();
+            p_ = o.p_; size_ = o.size_; cap_ = o.cap_; pinned_ = o.pinned_;
+            o.p_ = nullptr; o.size_ = o.cap_ = 0; o.pinned_ = false;
+        }
+        return *this;
+    }
     ~Bytes() { release(); }
     void reset(size_t n);                    // contents undefined afterwards
     void truncate(size_t n) { if (n < size_) size_ = n; }
@@ -148,6 +158,7 @@ class Bytes {
     uint8_t *data() { return p_; }
     const uint8_t *data() const { return p_; }
     size_t size() const { return size_; }
+    static void TrimCache();                 // unpin the released buffers kept for reuse (lzma_reader.cpp, PinnedCache)
   private:
     void release();
     uint8_t *p_ = nullptr;
@@ -195,10 +206,11 @@ std::pair<std::unique_ptr<io::ReadCloser>, error> NewLZMADecompressorForSevenZip
 // ---- reader2.go ---------------------------------------------------------------------------------
 class Reader2 : public io::Reader {
   public:
+    Reader2();
     ~Reader2();
     std::pair<int, error> Read(uint8_t *p, size_t len) override;
     size_t wave_bytes = (size_t)1 << 30;   // decoded bytes per GPU call (at least one unit).  A wave takes as long as its longest unit (~100 ms per MiB of text), however many units it has: large waves are what gives throughput
-    bool decode_ahead = true;         // decode wave k+1 on a second thread while wave k is being served
+    bool decode_ahead = true;         // wave k+1 is decoded and wave k+2 read from the input while wave k is being served
 
   private:
     friend std::pair<std::unique_ptr<Reader2>, error> NewReader2(io::Reader &, int, std::shared_ptr<Engine>);
@@ -207,23 +219,31 @@ class Reader2 : public io::Reader {
     error initialize();   // validateDictSize + the first chunk header, reader2.go:77-173
     bool fill(size_t need);
     bool independentFrom(size_t pos);
-    bool nextWave(std::vector<uint8_t> &wave);
+    bool nextWave(size_t &start, size_t &end, bool &term);
     struct Wave {
-        Bytes out;
+        Bytes in;            // the wave's compressed bytes, terminated (page-locked when large: read by the kernel in place)
+        size_t in_len = 0;
+        Bytes out;           // its decoded bytes
         error err;
         bool last = false;
+        double cut_ms = 0;
     };
-    std::unique_ptr<Wave> decodeWave();   // reads the next wave's input and decodes it (runs on the ahead thread too)
-    void startAhead();
+    std::unique_ptr<Wave> cutWave(std::unique_ptr<Wave> w);                // stage 1: input -> wave bytes
+    std::unique_ptr<Wave> decodeWave(std::unique_ptr<Wave> w, Bytes out);  // stage 2: one GPU call
+    void advance(std::unique_ptr<Wave> done);                              // stage 3 takes the next decoded wave
+    void startPipeline();
+    struct Mailbox;
     io::Reader *in_ = nullptr;
     std::shared_ptr<Engine> eng_;
     uint32_t dict_ = 0;
-    std::vector<uint8_t> buf_;            // (touched only by whoever runs decodeWave: never two at a time)
+    std::vector<uint8_t> buf_;            // input read ahead (touched only by the cut in flight: never two at a time)
     size_t rd_ = 0, pos_ = 0;
     bool in_eof_ = false;
     std::unique_ptr<Wave> cur_;           // being served
-    std::unique_ptr<Wave> spare_;         // delivered: its buffer goes to the next decodeWave
-    std::future<std::unique_ptr<Wave>> next_;
+    std::unique_ptr<Mailbox> cut_box_, dec_box_;   // cutter -> decoder -> Read
+    std::thread cutter_, decoder_;
+    std::mutex free_mu_;
+    std::vector<Bytes> free_in_, free_out_;        // buffers of delivered waves
 };
 
 std::pair<std::unique_ptr<Reader2>, error> NewReader2(io::Reader &inStream, int dictSize, std::shared_ptr<Engine> eng = nullptr);

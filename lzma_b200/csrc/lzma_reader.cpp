@@ -4,6 +4,9 @@
 #include "lzma_reader.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -129,9 +132,52 @@ size_t read_exact(io::Reader *r, uint8_t *p, size_t n) {
 }  // namespace
 
 // ---------------------------------------------------------------- Bytes
+// Page-locking memory costs ~0.4 s per GiB (every page is faulted in and pinned), as much as decoding it: released
+// buffers are kept for the next reader of the process (a handful, bounded in bytes) instead of being unpinned.
+namespace {
+struct PinnedCache {
+    std::mutex mu;
+    std::vector<std::pair<uint8_t *, size_t>> free_;   // (pointer, capacity)
+    size_t bytes = 0;
+    static constexpr size_t kMaxBytes = (size_t)6 << 30, kMaxBuffers = 6;
+    ~PinnedCache() { /* process exit: the driver is shutting down, leave the pages to the OS */ }
+    uint8_t *take(size_t want, size_t *cap) {
+        std::lock_guard<std::mutex> lock(mu);
+        size_t best = free_.size();
+        for (size_t i = 0; i < free_.size(); i++)
+            if (free_[i].second >= want && (best == free_.size() || free_[i].second < free_[best].second)) best = i;
+        if (best == free_.size()) return nullptr;
+        uint8_t *p = free_[best].first;
+        *cap = free_[best].second;
+        bytes -= *cap;
+        free_.erase(free_.begin() + best);
+        return p;
+    }
+    bool give(uint8_t *p, size_t cap) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (free_.size() >= kMaxBuffers || bytes + cap > kMaxBytes) return false;
+        free_.push_back({p, cap});
+        bytes += cap;
+        return true;
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lock(mu);
+        for (auto &b : free_) lzgpu_free_pinned(b.first);
+        free_.clear();
+        bytes = 0;
+    }
+};
+PinnedCache &pinned_cache() {
+    static PinnedCache *c = new PinnedCache();   // never destroyed: see ~PinnedCache
+    return *c;
+}
+}  // namespace
+
+void Bytes::TrimCache() { pinned_cache().trim(); }
+
 void Bytes::release() {
     if (p_) {
-        if (pinned_) lzgpu_free_pinned(p_);
+        if (pinned_) { if (!pinned_cache().give(p_, cap_)) lzgpu_free_pinned(p_); }
         else free(p_);
     }
     p_ = nullptr;
@@ -143,6 +189,9 @@ void Bytes::reset(size_t n) {
     release();
     const size_t want = std::max<size_t>(n, 16);
     if (want >= (32u << 20)) {
+        size_t cap = 0;
+        p_ = pinned_cache().take(want, &cap);
+        if (p_) { pinned_ = true; cap_ = cap; size_ = n; return; }
         p_ = static_cast<uint8_t *>(lzgpu_alloc_pinned(want));
         pinned_ = p_ != nullptr;
     }
@@ -458,7 +507,7 @@ error Reader2::initialize() {
 
 bool Reader2::fill(size_t need) {   // at least `need` unread bytes in buf_ (false: the input ended first)
     while (buf_.size() - rd_ < need && !in_eof_) {
-        const size_t want = std::max<size_t>(1 << 20, need - (buf_.size() - rd_));
+        const size_t want = std::max<size_t>(4 << 20, need - (buf_.size() - rd_));
         const size_t old = buf_.size();
         buf_.resize(old + want);
         auto [n, e] = in_->Read(buf_.data() + old, want);
@@ -484,54 +533,75 @@ bool Reader2::independentFrom(size_t pos) {
 }
 
 // Walk chunk headers (reader2.go:100-214) from rd_ until wave_bytes of output are covered and the next chunk starts
-// a unit that inherits nothing.  Returns true when this wave is the stream's last.
-bool Reader2::nextWave(std::vector<uint8_t> &wave) {
-    const size_t start = rd_;
+// a unit that inherits nothing.  The wave is buf_[start, end) -- decoded where it lies, no copy -- and needs a 0x00
+// terminator written at buf_[end] when `term` (the byte there is the next wave's first control byte: the caller saves
+// and restores it).  Returns true when this wave is the stream's last.
+bool Reader2::nextWave(size_t &start, size_t &end, bool &term) {
+    start = rd_;
+    term = false;
     size_t pos = rd_, out = 0;
     bool first = true;
     for (;;) {
         rd_ = pos;
-        if (!fill(1)) { wave.assign(buf_.begin() + start, buf_.end()); rd_ = buf_.size(); return true; }   // ran off the input: the scanner reports it
+        if (!fill(1)) { end = buf_.size(); rd_ = buf_.size(); return true; }   // ran off the input: the scanner reports it
         const uint8_t ctrl = buf_[pos];
         if (ctrl == 0 || (ctrl >= 3 && ctrl < 0x80)) {   // end of stream (0x03-0x7F too, reader2.go:185-198)
             rd_ = pos + 1;
-            wave.assign(buf_.begin() + start, buf_.begin() + pos + 1);
+            end = pos + 1;
             return true;
         }
         const bool enough = !first && out >= wave_bytes;
         const bool reset = ctrl >= 0xE0 || (ctrl == 1 && enough && independentFrom(pos));
         rd_ = pos;
-        if (reset && enough) {   // the wave ends before this chunk; terminate it
-            wave.assign(buf_.begin() + start, buf_.begin() + pos);
-            wave.push_back(0);
+        if (reset && enough) {   // the wave ends before this chunk; it is terminated there
+            end = pos;
+            term = true;
             return false;
         }
         const size_t hl = ctrl < 0x80 ? 3 : (ctrl < 0xC0 ? 5 : 6);
-        if (!fill(hl)) { wave.assign(buf_.begin() + start, buf_.end()); rd_ = buf_.size(); return true; }
+        if (!fill(hl)) { end = buf_.size(); rd_ = buf_.size(); return true; }
         size_t usz = (((size_t)buf_[pos + 1] << 8) | buf_[pos + 2]) + 1, payload;
         if (ctrl >= 0x80) {
             usz += (size_t)(ctrl & 0x1F) << 16;
             payload = (((size_t)buf_[pos + 3] << 8) | buf_[pos + 4]) + 1;
         } else payload = usz;
-        if (!fill(hl + payload)) { wave.assign(buf_.begin() + start, buf_.end()); rd_ = buf_.size(); return true; }
+        if (!fill(hl + payload)) { end = buf_.size(); rd_ = buf_.size(); return true; }
         pos += hl + payload;
         out += usz;
         first = false;
     }
 }
 
-std::unique_ptr<Reader2::Wave> Reader2::decodeWave() {
-    // a delivered wave's buffer is reused (page-locked memory is dear to allocate): three rotate -- served, decoding, spare
-    std::unique_ptr<Wave> w = std::move(spare_);
+// Stage 1 of the reader's pipeline: find the next wave in the input (nextWave) and move its bytes, terminated, into
+// the wave's own buffer -- page-locked when large, so that the decode kernel reads it straight from host memory.
+// `w` brings the buffers of a delivered wave back into circulation.
+std::unique_ptr<Reader2::Wave> Reader2::cutWave(std::unique_ptr<Wave> w) {
     if (!w) w.reset(new Wave());
     w->err = nullptr;
-    w->last = false;
-    std::vector<uint8_t> wave;
-    const bool last = nextWave(wave);
-    if (rd_ > (8u << 20)) {   // drop what has been handed to the GPU
+    w->out.clear();
+    size_t start = 0, end = 0;
+    bool term = false;
+    const auto t0 = std::chrono::steady_clock::now();
+    w->last = nextWave(start, end, term);
+    const size_t n = end - start;
+    w->in.reset(n + 1 + 16);
+    if (n) memcpy(w->in.data(), buf_.data() + start, n);
+    w->in.data()[n] = 0;                              // terminator of a wave that is not the stream's last
+    w->in_len = n + (term ? 1 : 0);
+    if (rd_ > (1u << 20)) {   // drop what has been handed on (the tail that stays is small)
         buf_.erase(buf_.begin(), buf_.begin() + rd_);
         rd_ = 0;
     }
+    w->cut_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return w;
+}
+
+// Stage 2: scan the wave into units and decode them in one GPU call, into `out` (a delivered wave's buffer, or empty).
+std::unique_ptr<Reader2::Wave> Reader2::decodeWave(std::unique_ptr<Wave> w, Bytes out) {
+    static const bool trace = getenv("LZMA_READER_TRACE") != nullptr;   // phase times of every wave on stderr
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+    w->out = std::move(out);
     if (!eng_) {
         auto [e, err] = Engine::Default();
         if (err) { w->err = err; w->last = true; return w; }
@@ -540,15 +610,19 @@ std::unique_ptr<Reader2::Wave> Reader2::decodeWave() {
     std::vector<Unit> units(64);
     uint64_t total = 0;
     int32_t sst = 0;
-    int64_t n = lzgpu_scan_lzma2(wave.data(), wave.size(), dict_, units.data(), (int64_t)units.size(), &total, &sst);
+    int64_t n = lzgpu_scan_lzma2(w->in.data(), w->in_len, dict_, units.data(), (int64_t)units.size(), &total, &sst);
     if (n > (int64_t)units.size()) {
         units.resize((size_t)n);
-        n = lzgpu_scan_lzma2(wave.data(), wave.size(), dict_, units.data(), (int64_t)units.size(), &total, &sst);
+        n = lzgpu_scan_lzma2(w->in.data(), w->in_len, dict_, units.data(), (int64_t)units.size(), &total, &sst);
     }
     if (n < 0) { w->err = errors::New(std::string("lzgpu: ") + lzgpu_last_error()); w->last = true; return w; }
     units.resize((size_t)n);
+    const double t_scan = ms();
     w->out.reset((size_t)std::max<uint64_t>(total, 16));
-    auto [res, err] = eng_->DecodeBatch(units, wave.data(), wave.size(), w->out.data(), w->out.size());
+    const double t_alloc = ms();
+    auto [res, err] = eng_->DecodeBatch(units, w->in.data(), w->in_len, w->out.data(), w->out.size());
+    if (trace) fprintf(stderr, "[reader2] wave of %zu units, %.0f MiB: cut %.1f ms, scan %.1f, buffer %.1f, decode %.1f\n", units.size(),
+                       total / 1048576.0, w->cut_ms, t_scan, t_alloc - t_scan, ms() - t_alloc);
     if (err) { w->out.clear(); w->err = err; w->last = true; return w; }
     // the bytes of the units before the first failing one are delivered with the failure, as the reference's
     // reader would have delivered them
@@ -560,33 +634,110 @@ std::unique_ptr<Reader2::Wave> Reader2::decodeWave() {
     }
     w->out.truncate((size_t)n_out);
     w->err = Engine::StatusError(status);
-    w->last = last || w->err != nullptr;
+    w->last = w->last || w->err != nullptr;
     return w;
 }
 
-// Wave k+1 is read and decoded on another thread while wave k is being served: a steady reader sees the GPU's
-// throughput rather than decode and delivery taking turns (the reference streams chunk by chunk, reader2.go:216-250;
-// here a Read would otherwise block for a whole wave).  Only that thread touches in_ / buf_ until its result is taken.
-void Reader2::startAhead() {
-    if (decode_ahead) next_ = std::async(std::launch::async, [this]() { return decodeWave(); });
+// Three stages run at once (the reference streams chunk by chunk, reader2.go:216-250; here a Read would otherwise
+// block for a whole wave): wave k is being served to the caller, wave k+1 is being decoded by the GPU, wave k+2 is
+// being read from the input -- a steady reader sees the GPU's throughput.  A cutter thread and a decoder thread hand
+// waves on through one-slot mailboxes; a stage starts its next wave only when its mailbox is empty, so at most three
+// waves exist.  The buffers of delivered waves go back to the stages through `free_in_` / `free_out_`.
+struct Reader2::Mailbox {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::unique_ptr<Wave> slot;
+    bool closed = false;   // the producer will not put anything more
+    bool stop = false;     // the reader is going away
+    bool wait_empty() {    // producer: before starting on the next wave
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return !slot || stop; });
+        return !stop;
+    }
+    void put(std::unique_ptr<Wave> w, bool last) {
+        std::lock_guard<std::mutex> lk(mu);
+        slot = std::move(w);
+        closed = last;
+        cv.notify_all();
+    }
+    std::unique_ptr<Wave> take() {   // consumer: null when the producer is done
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return slot || closed || stop; });
+        std::unique_ptr<Wave> w = std::move(slot);
+        cv.notify_all();
+        return w;
+    }
+    void shutdown() {
+        std::lock_guard<std::mutex> lk(mu);
+        stop = true;
+        cv.notify_all();
+    }
+};
+
+void Reader2::startPipeline() {
+    cut_box_.reset(new Mailbox());
+    dec_box_.reset(new Mailbox());
+    cutter_ = std::thread([this]() {
+        for (;;) {
+            if (!cut_box_->wait_empty()) return;
+            std::unique_ptr<Wave> w(new Wave());
+            { std::lock_guard<std::mutex> lk(free_mu_); if (!free_in_.empty()) { w->in = std::move(free_in_.back()); free_in_.pop_back(); } }
+            w = cutWave(std::move(w));
+            const bool last = w->last;
+            cut_box_->put(std::move(w), last);
+            if (last) return;
+        }
+    });
+    decoder_ = std::thread([this]() {
+        for (;;) {
+            if (!dec_box_->wait_empty()) return;
+            std::unique_ptr<Wave> w = cut_box_->take();
+            if (!w) { dec_box_->put(nullptr, true); return; }
+            Bytes out;
+            { std::lock_guard<std::mutex> lk(free_mu_); if (!free_out_.empty()) { out = std::move(free_out_.back()); free_out_.pop_back(); } }
+            w = decodeWave(std::move(w), std::move(out));
+            { std::lock_guard<std::mutex> lk(free_mu_); free_in_.push_back(std::move(w->in)); }   // the input is done with
+            const bool last = w->last;
+            dec_box_->put(std::move(w), last);
+            if (last) { cut_box_->shutdown(); return; }   // (an error ends the stream: the cutter need not go on)
+        }
+    });
 }
 
+void Reader2::advance(std::unique_ptr<Wave> done) {
+    if (done) { std::lock_guard<std::mutex> lk(free_mu_); free_out_.push_back(std::move(done->out)); }
+    pos_ = 0;
+    if (!decode_ahead) {   // one wave at a time, on the caller's thread
+        std::unique_ptr<Wave> w(new Wave());
+        if (!free_in_.empty()) { w->in = std::move(free_in_.back()); free_in_.pop_back(); }
+        Bytes out;
+        if (!free_out_.empty()) { out = std::move(free_out_.back()); free_out_.pop_back(); }
+        cur_ = decodeWave(cutWave(std::move(w)), std::move(out));
+        free_in_.push_back(std::move(cur_->in));
+        return;
+    }
+    if (!dec_box_) startPipeline();
+    cur_ = dec_box_->take();
+    if (!cur_) {   // (cannot happen: the decoder always delivers a last wave)
+        cur_.reset(new Wave());
+        cur_->last = true;
+    }
+}
+
+Reader2::Reader2() = default;
+
 Reader2::~Reader2() {
-    if (next_.valid()) next_.wait();
+    if (dec_box_) {
+        cut_box_->shutdown();
+        dec_box_->shutdown();
+        if (cutter_.joinable()) cutter_.join();
+        if (decoder_.joinable()) decoder_.join();
+    }
 }
 
 std::pair<int, error> Reader2::Read(uint8_t *p, size_t len) {   // reader2.go:216-250
-    if (!cur_) {
-        cur_ = decodeWave();
-        if (!cur_->last) startAhead();
-    }
-    while (pos_ == cur_->out.size() && !cur_->last && len) {   // previous wave delivered: the next one
-        std::unique_ptr<Wave> done = std::move(cur_);
-        cur_ = next_.valid() ? next_.get() : decodeWave();
-        spare_ = std::move(done);                              // (no decodeWave is running here: the ahead thread has finished)
-        pos_ = 0;
-        if (!cur_->last) startAhead();
-    }
+    if (!cur_) advance(nullptr);
+    while (pos_ == cur_->out.size() && !cur_->last && len) advance(std::move(cur_));   // previous wave delivered: the next one
     const size_t n = std::min(len, cur_->out.size() - pos_);
     if (n) {
         memcpy(p, cur_->out.data() + pos_, n);
