@@ -28,6 +28,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -166,6 +167,24 @@ class Bytes {
     bool pinned_ = false;
 };
 
+// a growing byte buffer over Bytes (so that large ones are page-locked and come from the process-wide cache)
+class InBuf {
+  public:
+    size_t size() const { return len_; }
+    uint8_t *data() { return mem_.data(); }
+    uint8_t &operator[](size_t i) { return mem_.data()[i]; }
+    void assign(const uint8_t *p, size_t n) { len_ = 0; append(p, n); }
+    void append(const uint8_t *p, size_t n) { reserve(len_ + n); if (n) memcpy(mem_.data() + len_, p, n); len_ += n; }
+    void reserve(size_t cap);                 // keeps the contents
+    void set_size(size_t n) { len_ = n; }     // n <= capacity
+    size_t capacity() const { return cap_; }
+    Bytes release() { len_ = cap_ = 0; return std::move(mem_); }
+    void adopt(Bytes b, size_t cap) { mem_ = std::move(b); cap_ = cap; len_ = 0; }
+  private:
+    Bytes mem_;
+    size_t len_ = 0, cap_ = 0;
+};
+
 // ---- reader1.go ---------------------------------------------------------------------------------
 std::tuple<uint8_t, uint8_t, uint8_t, error> DecodeProp(uint8_t d);        // (lc, pb, lp, err)
 std::pair<uint32_t, error> DecodeDictSize(const uint8_t properties[4]);
@@ -221,7 +240,8 @@ class Reader2 : public io::Reader {
     bool independentFrom(size_t pos);
     bool nextWave(size_t &start, size_t &end, bool &term);
     struct Wave {
-        Bytes in;            // the wave's compressed bytes, terminated (page-locked when large: read by the kernel in place)
+        Bytes in;            // holds the wave's compressed bytes, terminated, at [in_off, in_off + in_len) (page-locked when
+        size_t in_off = 0;   //  large: the kernel reads them in place)
         size_t in_len = 0;
         Bytes out;           // its decoded bytes
         error err;
@@ -236,7 +256,7 @@ class Reader2 : public io::Reader {
     io::Reader *in_ = nullptr;
     std::shared_ptr<Engine> eng_;
     uint32_t dict_ = 0;
-    std::vector<uint8_t> buf_;            // input read ahead (touched only by the cut in flight: never two at a time)
+    InBuf buf_;                           // input read ahead (touched only by the cut in flight: never two at a time)
     size_t rd_ = 0, pos_ = 0;
     bool in_eof_ = false;
     std::unique_ptr<Wave> cur_;           // being served

@@ -139,7 +139,7 @@ struct PinnedCache {
     std::mutex mu;
     std::vector<std::pair<uint8_t *, size_t>> free_;   // (pointer, capacity)
     size_t bytes = 0;
-    static constexpr size_t kMaxBytes = (size_t)6 << 30, kMaxBuffers = 6;
+    static constexpr size_t kMaxBytes = (size_t)8 << 30, kMaxBuffers = 8;
     ~PinnedCache() { /* process exit: the driver is shutting down, leave the pages to the OS */ }
     uint8_t *take(size_t want, size_t *cap) {
         std::lock_guard<std::mutex> lock(mu);
@@ -188,7 +188,11 @@ void Bytes::reset(size_t n) {
     if (n <= cap_) { size_ = n; return; }
     release();
     const size_t want = std::max<size_t>(n, 16);
-    if (want >= (32u << 20)) {
+    // LZMA_READER_NO_PIN=1: ordinary memory only.  Page-locking is what lets the output stream back while the kernel
+    // runs and the input be read in place, but the first use of a buffer costs ~1 s per GiB: a one-shot tool that
+    // decodes a single stream and exits is better off without, a long-lived process keeps its buffers.
+    static const bool no_pin = getenv("LZMA_READER_NO_PIN") != nullptr;
+    if (want >= (32u << 20) && !no_pin) {
         size_t cap = 0;
         p_ = pinned_cache().take(want, &cap);
         if (p_) { pinned_ = true; cap_ = cap; size_ = n; return; }
@@ -486,12 +490,12 @@ error Reader2::initialize() {
     if (dict_ < (1u << 12)) dict_ = 8u << 20;   // reader2.go:88-91
     uint8_t c;
     if (read_exact(in_, &c, 1) < 1) return io::ErrUnexpectedEOF;   // reader2.go:103-110
-    buf_.assign(1, c);
+    buf_.assign(&c, 1);
     if (c == 0 || (c >= 3 && c < 0x80)) return nullptr;
     const size_t hl = c < 0x80 ? 3 : (c < 0xC0 ? 5 : 6);
     uint8_t rest[6];
     const size_t got = read_exact(in_, rest, hl - 1);
-    buf_.insert(buf_.end(), rest, rest + got);
+    buf_.append(rest, got);
     if (got < hl - 1) return io::ErrUnexpectedEOF;   // reader2.go:121-128
     if (c >= 0x80) {
         // first LZMA chunk: NewReader1ForReader2 -> DecodeProp + rangeDec.Init (reader2.go:146-153)
@@ -499,7 +503,7 @@ error Reader2::initialize() {
         if (prop >= 225) return ErrIncorrectProperties;
         uint8_t pre;
         if (read_exact(in_, &pre, 1) < 1) return errors::Errorf("rangeDec.Init", io::EOF_);
-        buf_.push_back(pre);
+        buf_.append(&pre, 1);
         if (pre != 0) return errors::Errorf("rangeDec.Init", ErrResultError);
     }
     return nullptr;
@@ -509,9 +513,11 @@ bool Reader2::fill(size_t need) {   // at least `need` unread bytes in buf_ (fal
     while (buf_.size() - rd_ < need && !in_eof_) {
         const size_t want = std::max<size_t>(4 << 20, need - (buf_.size() - rd_));
         const size_t old = buf_.size();
-        buf_.resize(old + want);
+        // an input buffer is sized once for a whole wave (text compresses 3-4x: half the wave's output is ample), so that
+        // the same few page-locked buffers circulate for the life of the reader -- and, through the cache, of the process
+        buf_.reserve(std::max(old + want, std::min<size_t>(wave_bytes / 2, (size_t)1 << 30) + (64u << 10)));
         auto [n, e] = in_->Read(buf_.data() + old, want);
-        buf_.resize(old + (n > 0 ? (size_t)n : 0));
+        buf_.set_size(old + (n > 0 ? (size_t)n : 0));
         if (e || n <= 0) in_eof_ = true;
     }
     return buf_.size() - rd_ >= need;
@@ -583,17 +589,34 @@ std::unique_ptr<Reader2::Wave> Reader2::cutWave(std::unique_ptr<Wave> w) {
     bool term = false;
     const auto t0 = std::chrono::steady_clock::now();
     w->last = nextWave(start, end, term);
-    const size_t n = end - start;
-    w->in.reset(n + 1 + 16);
-    if (n) memcpy(w->in.data(), buf_.data() + start, n);
-    w->in.data()[n] = 0;                              // terminator of a wave that is not the stream's last
-    w->in_len = n + (term ? 1 : 0);
-    if (rd_ > (1u << 20)) {   // drop what has been handed on (the tail that stays is small)
-        buf_.erase(buf_.begin(), buf_.begin() + rd_);
-        rd_ = 0;
-    }
+    // The wave stays where it was read: the input buffer itself goes to the decoder, and what was read beyond the
+    // wave (a few MiB at most) moves to a new input buffer -- w->in, a delivered wave's, when it is large enough.
+    const size_t tail = buf_.size() - end;
+    InBuf nb;
+    const size_t want = std::max<size_t>(tail + (1u << 20), std::min<size_t>(wave_bytes / 2, (size_t)1 << 30) + (64u << 10));
+    if (w->in.size() >= want) { const size_t c = w->in.size(); nb.adopt(std::move(w->in), c); }
+    nb.reserve(want);
+    nb.append(buf_.data() + end, tail);
+    buf_.reserve(end + 1);
+    buf_[end] = 0;                                    // terminator of a wave that is not the stream's last
+    w->in_off = start;
+    w->in_len = end - start + (term ? 1 : 0);
+    w->in = buf_.release();
+    buf_ = std::move(nb);
+    rd_ = 0;
     w->cut_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return w;
+}
+
+void InBuf::reserve(size_t cap) {
+    if (cap <= cap_) return;
+    size_t want = std::max<size_t>(cap, cap_ * 2);
+    if (want < 4096) want = 4096;
+    Bytes nb;
+    nb.reset(want);
+    if (len_) memcpy(nb.data(), mem_.data(), len_);
+    mem_ = std::move(nb);
+    cap_ = want;
 }
 
 // Stage 2: scan the wave into units and decode them in one GPU call, into `out` (a delivered wave's buffer, or empty).
@@ -610,17 +633,18 @@ std::unique_ptr<Reader2::Wave> Reader2::decodeWave(std::unique_ptr<Wave> w, Byte
     std::vector<Unit> units(64);
     uint64_t total = 0;
     int32_t sst = 0;
-    int64_t n = lzgpu_scan_lzma2(w->in.data(), w->in_len, dict_, units.data(), (int64_t)units.size(), &total, &sst);
+    const uint8_t *wave = w->in.data() + w->in_off;
+    int64_t n = lzgpu_scan_lzma2(wave, w->in_len, dict_, units.data(), (int64_t)units.size(), &total, &sst);
     if (n > (int64_t)units.size()) {
         units.resize((size_t)n);
-        n = lzgpu_scan_lzma2(w->in.data(), w->in_len, dict_, units.data(), (int64_t)units.size(), &total, &sst);
+        n = lzgpu_scan_lzma2(wave, w->in_len, dict_, units.data(), (int64_t)units.size(), &total, &sst);
     }
     if (n < 0) { w->err = errors::New(std::string("lzgpu: ") + lzgpu_last_error()); w->last = true; return w; }
     units.resize((size_t)n);
     const double t_scan = ms();
     w->out.reset((size_t)std::max<uint64_t>(total, 16));
     const double t_alloc = ms();
-    auto [res, err] = eng_->DecodeBatch(units, w->in.data(), w->in_len, w->out.data(), w->out.size());
+    auto [res, err] = eng_->DecodeBatch(units, wave, w->in_len, w->out.data(), w->out.size());
     if (trace) fprintf(stderr, "[reader2] wave of %zu units, %.0f MiB: cut %.1f ms, scan %.1f, buffer %.1f, decode %.1f\n", units.size(),
                        total / 1048576.0, w->cut_ms, t_scan, t_alloc - t_scan, ms() - t_alloc);
     if (err) { w->out.clear(); w->err = err; w->last = true; return w; }
