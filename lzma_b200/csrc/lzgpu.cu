@@ -335,6 +335,7 @@ struct lzgpu_plan {
     bool launched = false;
     bool borrowed = false;                // d_units / d_order / d_results live in the device's descriptor arena
     int variant = 0;
+    int max_ctas_per_sm = 0;              // 0: as many as fit (14 at lc3 lp0 pb2)
 };
 
 extern "C" int lzgpu_ctx_create(const int *devices, int n_devices, lzgpu_ctx **out) {
@@ -414,6 +415,7 @@ static int plan_create_impl(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *uni
     p->ctx = ctx;
     p->dev_index = dev_index;
     p->variant = decoder_variant();
+    if (const char *e = getenv("LZGPU_MAX_CTAS_PER_SM")) p->max_ctas_per_sm = atoi(e);
     p->n = n;
     p->in_size = in_size;
     p->out_size = out_size;
@@ -541,8 +543,15 @@ extern "C" int lzgpu_plan_launch(lzgpu_plan *p, const uint8_t *d_in, uint8_t *d_
         a.slot0 = L.slot0;
         a.stage_off = (uint32_t)probs_elems(L.lit_bits, L.lit_global, L.pb2);
         a.progress = p->d_progress;
-        if (L.lit_global) launch_decode<true>(p->variant, false, L.count, L.smem, st, a);
-        else launch_decode<false>(p->variant, L.pb2, L.count, L.smem, st, a);
+        size_t smem = L.smem;
+        if (p->max_ctas_per_sm >= 5) {
+            // occupancy cap (experiments, and the single-wave heuristic of plan_create): asking for more shared memory
+            // than a unit needs is how a launch of one-warp CTAs limits how many of them share an SM
+            const size_t want = ((233472u / (unsigned)p->max_ctas_per_sm) - 1024u) & ~(size_t)15;
+            if (want > smem && want <= 48u * 1024u) smem = want;
+        }
+        if (L.lit_global) launch_decode<true>(p->variant, false, L.count, smem, st, a);
+        else launch_decode<false>(p->variant, L.pb2, L.count, smem, st, a);
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaEventRecord(p->ev1, st));
