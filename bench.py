@@ -495,7 +495,7 @@ def run_config4(env: Env):
                          "LZMA1, raw LZMA2 with dictionary resets and uncompressed chunks, incompressible data, the reference's "
                          "test assets, 60+ corrupt / truncated / bad-header streams"),
             "units_total": n, "streams": len(items), "ms": t_best * 1e3, "value": dec_bytes / t_best / 1e9, "unit": "GB/s",
-            "timing": "end to end through lzgpu_decode_batch with pinned host buffers (best of 3 calls); a parity case: the batch is as slow as its longest unit",
+            "timing": "end to end through lzgpu_decode_batch with pinned host buffers (best of 3 calls); a parity case: the batch is as slow as its longest unit -- the reference's own asset randomfile.dat.lzma, 1 MiB of incompressible data in ONE stream (250 ms on one warp); the table classes' launches run side by side",
             "decompressed_bytes_total": dec_bytes, "kernel_ms": st.kernel_ms, "gpu_launches": int(st.launches),
             "outcomes_by_oracle_status": kinds,
             "verified": f"status, error site (LZMA1) and decoded bytes of all {len(items)} streams == oracle; 0 mismatches"}

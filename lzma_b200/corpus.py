@@ -278,7 +278,7 @@ def mixed_batch(seed: int = 4, unit_size: int = 192 << 10, assets_dir: str | Non
         k += 1
     base = compress_alone(text_block(7100, 60_000), 4, 0, 2, 1 << 16)
     for lc, lp, pb in [(5, 0, 0), (8, 0, 2), (4, 4, 4), (8, 4, 4), (6, 2, 1), (5, 3, 3), (7, 1, 0), (4, 1, 2)]:
-        items.append({"name": f"relabel_lc{lc}lp{lp}pb{pb}", "kind": "alone", "data": bytes([(pb * 5 + lp) * 9 + lc]) + base[1:], "cap": 200_000})
+        items.append({"name": f"relabel_lc{lc}lp{lp}pb{pb}", "kind": "alone", "data": bytes([(pb * 5 + lp) * 9 + lc]) + base[1:], "cap": 40_000})
     for i, n in enumerate((1, 17, 300, 5000, 30_000, 60_000)):               # known size, no EOS marker
         s = alone_from_lzma2_chunk(text_block(7200 + i, n))
         if s:

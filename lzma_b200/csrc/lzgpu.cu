@@ -287,6 +287,10 @@ struct DevState {
     // grow-only staging for the host-buffer entry point
     uint8_t *d_in = nullptr, *d_out = nullptr;
     uint64_t in_cap = 0, out_cap = 0;
+    // launches of different table classes of one batch run side by side (fork / join around the caller's stream)
+    static constexpr int kAux = 4;
+    cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fork_ev = nullptr, join_ev[kAux] = {nullptr, nullptr, nullptr, nullptr};
     // streamed D2H: second stream, host-mapped progress counters (grow-only)
     cudaStream_t copy_stream = nullptr;
     uint32_t *h_progress = nullptr, *d_progress = nullptr;
@@ -365,6 +369,11 @@ extern "C" void lzgpu_ctx_destroy(lzgpu_ctx *c) {
         cudaSetDevice(d.device);
         if (d.stream) cudaStreamDestroy(d.stream);
         if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
+        for (int k = 0; k < DevState::kAux; k++) {
+            if (d.aux[k]) cudaStreamDestroy(d.aux[k]);
+            if (d.join_ev[k]) cudaEventDestroy(d.join_ev[k]);
+        }
+        if (d.fork_ev) cudaEventDestroy(d.fork_ev);
         if (d.h_progress) cudaFreeHost(d.h_progress);
         if (d.h_tails) cudaFreeHost(d.h_tails);
         if (d.d_desc) cudaFree(d.d_desc);
@@ -530,7 +539,25 @@ extern "C" int lzgpu_plan_launch(lzgpu_plan *p, const uint8_t *d_in, uint8_t *d_
     CUDA_TRY(cudaSetDevice(ds.device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ds.stream;
     CUDA_TRY(cudaEventRecord(p->ev0, st));
+    // A mixed batch has one launch per table class (literal-table size x posState-table size), and a launch lasts as
+    // long as its longest unit: classes are independent, so they run side by side on auxiliary streams, forked from
+    // and joined back into the caller's stream.  (Launches that share the HBM literal workspace stay on one stream.)
+    const bool fork = p->launches.size() > 1;
+    if (fork) {
+        if (!ds.fork_ev) {
+            CUDA_TRY(cudaEventCreateWithFlags(&ds.fork_ev, cudaEventDisableTiming));
+            for (int k = 0; k < DevState::kAux; k++) {
+                CUDA_TRY(cudaStreamCreateWithFlags(&ds.aux[k], cudaStreamNonBlocking));
+                CUDA_TRY(cudaEventCreateWithFlags(&ds.join_ev[k], cudaEventDisableTiming));
+            }
+        }
+        CUDA_TRY(cudaEventRecord(ds.fork_ev, st));
+        for (int k = 0; k < DevState::kAux; k++) CUDA_TRY(cudaStreamWaitEvent(ds.aux[k], ds.fork_ev, 0));
+    }
+    int rr = 1;
     for (const Launch &L : p->launches) {
+        cudaStream_t ls = st;
+        if (fork) { ls = L.lit_global ? ds.aux[0] : ds.aux[rr]; if (!L.lit_global) rr = rr % (DevState::kAux - 1) + 1; }
         KArgs a;
         a.units = p->d_units;
         a.order = p->d_order;
@@ -550,10 +577,15 @@ extern "C" int lzgpu_plan_launch(lzgpu_plan *p, const uint8_t *d_in, uint8_t *d_
             const size_t want = ((233472u / (unsigned)p->max_ctas_per_sm) - 1024u) & ~(size_t)15;
             if (want > smem && want <= 48u * 1024u) smem = want;
         }
-        if (L.lit_global) launch_decode<true>(p->variant, false, L.count, smem, st, a);
-        else launch_decode<false>(p->variant, L.pb2, L.count, smem, st, a);
+        if (L.lit_global) launch_decode<true>(p->variant, false, L.count, smem, ls, a);
+        else launch_decode<false>(p->variant, L.pb2, L.count, smem, ls, a);
         CUDA_TRY(cudaGetLastError());
     }
+    if (fork)
+        for (int k = 0; k < DevState::kAux; k++) {
+            CUDA_TRY(cudaEventRecord(ds.join_ev[k], ds.aux[k]));
+            CUDA_TRY(cudaStreamWaitEvent(st, ds.join_ev[k], 0));
+        }
     CUDA_TRY(cudaEventRecord(p->ev1, st));
     p->last_stream = st;
     p->launched = true;

@@ -213,11 +213,15 @@ LZ_DEV bool f2_enter(Dec &d, const uint8_t *gpos, uint8_t *inbuf) {
     const uint64_t span = (uint64_t)(d.in_end - g0);
     const uint32_t avail = span >= kF2Stage ? kF2Stage : ((uint32_t)span & ~15u);   // whole 16-byte chunks of this unit only
     const uint32_t l = LZ_LANE();
-    {   // predicated, not branched (avail >= 112: lanes beyond it re-load chunk 0 and do not store)
+    {   // one 16-byte cp.async (LDGSTS) per lane, global -> shared with no register in between; predicated, not
+        // branched (avail >= 112: lanes beyond it name chunk 0 and copy nothing).  It is awaited right away -- a
+        // second stage to fill ahead would cost the 14th unit per SM, and a refill is 0.1 % of a unit's time.
         const bool live = 16u * l + 16u <= avail;
-        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(g0) + (live ? l : 0u));
-        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n\t}"
-                     : : "r"(d.sIn + 16u * l), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w), "r"((uint32_t)live) : "memory");
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t"
+                     "@q cp.async.cg.shared.global [%0], [%1], 16;\n\t"
+                     "cp.async.commit_group;\n\t"
+                     "cp.async.wait_group 0;\n\t}"
+                     : : "r"(d.sIn + 16u * l), "l"(g0 + 16u * (live ? l : 0u)), "r"((uint32_t)live) : "memory");
         const uint8_t *pf = g0 + kF2Stage + 128u * (l & 3u);
         if (pf >= d.in_end) pf = g0;                 // (same prefetch from every lane group: harmless)
         LZ_PREFETCH_L2(pf);
