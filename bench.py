@@ -43,9 +43,10 @@ sys.path.insert(0, ROOT)
 STREAM_SIZE = 1 << 20
 METRIC = "decompressed GB/s (batch, device-timed)"
 # name of the dominant kernel as ncu prints it (variant 33 | V_PB2 = 97: the V_CHAIN decoder with compact posState
-# tables), and the tag profiles/traffic.json must carry for its dram-bytes figure to be quoted
-KERNEL_NAME = "void lzgpu_decode_kernel<0, 97>(KArgs)"
-KERNEL_TAG = "r02"
+# tables, under the SM-resident scheduler), and the tag profiles/traffic.json must carry for its dram-bytes figure to
+# be quoted
+KERNEL_NAME = "void lzgpu_sm_kernel<97>(KArgs, SmArgs)"
+KERNEL_TAG = "r02b"
 
 
 def log(*a):

@@ -68,6 +68,304 @@ __global__ void __launch_bounds__(32, LZGPU_MIN_CTAS) lzgpu_decode_kernel(const 
     else run_unit_lzma1<kV>(u, io, P, L, res);
 }
 
+// ------------------------------------------------------------------ SM-resident scheduler
+// One CTA per SM holds up to 14 units (their tables in its shared memory) and as many warps; which warp decodes which
+// unit changes while the kernel runs.  Why: a warp is tied to one of the SM's four sub-partitions (warp id mod 4), and a
+// sub-partition that holds 4 warps gives each of them 3/4 of the issue rate the warps of a 3-warp sub-partition get.
+// With one-warp CTAs and 2 048 units per GPU (BASELINE config 5 sharded over 8 GPUs: ONE wave, 13.8 units per SM) the
+// kernel lasts as long as the units that happened to land on the crowded sub-partitions, and when units finish at
+// different times the warps that are left stay where they are, however unevenly.  Here
+//   * a unit can leave its warp wherever the fast decoder refills its input stage (run_lzma, RUN_YIELD): its state goes
+//     to a save area next to its tables and any warp of the CTA can take it from there;
+//   * every `rotate_every` refills a warp offers its unit for exchange and takes the one another warp offers, so over
+//     their lifetime all units of the SM see the same mix of sub-partitions and advance at the SM's average rate;
+//   * when units finish, warps on a sub-partition that now has more active warps than its share hand their unit to an
+//     idle warp of a sub-partition with fewer (targets: the live units spread evenly over the four);
+//   * a warp whose unit is done takes the next unit of the launch from a global counter (longest compressed first,
+//     as before); the first wave is assigned statically (unit w * grid + cta), one unit of every size band per CTA.
+// LZMA1 units are time-sliced; an LZMA2 group runs to completion on the warp that started it (its chunk walk keeps
+// state outside Dec), but takes part in everything else.
+struct SmArgs {
+    uint32_t count;          // units of this launch (slots [slot0, slot0 + count) of `order`)
+    uint32_t n_slots;        // units resident per CTA = warps per CTA
+    uint32_t slot_bytes;     // shared memory of one slot: tables, stages, save area
+    uint32_t save_off;       // offset of the save area inside a slot
+    uint32_t rotate_every;   // refills between two exchange offers of a warp (0: never)
+    uint32_t *next;          // units started beyond the first wave (device counter, zeroed before the launch)
+};
+struct SmCtl {
+    uint32_t lock;
+    uint32_t live;           // units resident in this CTA and not finished
+    uint32_t dry;            // the launch has no more units to start
+    uint32_t q_head, q_tail; // ring of slots waiting for a warp
+    uint32_t sp_active[4];   // warps decoding, per sub-partition
+    uint32_t sp_over[4];     // that sub-partition has more active warps than its share while another has room
+    uint32_t uneven;         // the active warps are not spread evenly: exchanging units pays
+    uint32_t ring[16];
+};
+struct SmSaved {
+    Dec d;
+    WarpCopy wc;
+    const uint8_t *in;
+    uint8_t *out;
+    int32_t ui;
+};
+constexpr uint32_t kSmCtlBytes = 128;
+constexpr uint32_t kSmSaveBytes = (sizeof(SmSaved) + 15u) & ~15u;
+constexpr uint32_t kSmMaxSlots = 14;
+static_assert(sizeof(SmCtl) <= kSmCtlBytes, "SmCtl");
+
+__device__ __forceinline__ uint32_t sm_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+// Atomics are executed by ALL lanes (a predicated atom becomes a branch around it in SASS, and one divergent branch
+// anywhere makes ptxas bracket every branch of the decoder with convergence barriers): the lock is taken by whichever
+// lane's exchange reads 0, and the unit counter advances by 32 per fetch; a warp-wide minimum gives every lane the
+// same answer.
+__device__ __forceinline__ uint32_t sm_fetch_global(uint32_t *p) {   // returns 0, 1, 2, ... over the calls of all warps
+    uint32_t r;
+    asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(r) : "l"(p) : "memory");
+    return __reduce_min_sync(0xffffffffu, r) >> 5;
+}
+__device__ __forceinline__ void sm_lock(SmCtl *c) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(&c->lock);
+#ifdef LZGPU_SM_WATCHDOG
+    uint32_t spins = 0;
+#endif
+    for (;;) {
+        uint32_t r;
+        asm volatile("atom.shared.exch.b32 %0, [%1], 1;" : "=r"(r) : "r"(a) : "memory");
+        if (__reduce_min_sync(0xffffffffu, r) == 0u) break;
+        __nanosleep(40);
+#ifdef LZGPU_SM_WATCHDOG
+        if (++spins > 2000000u) asm volatile("trap;");
+#endif
+    }
+    __threadfence_block();
+}
+__device__ __forceinline__ void sm_unlock(SmCtl *c) {
+    __threadfence_block();
+    __syncwarp();
+    *(volatile uint32_t *)&c->lock = 0u;   // every lane, same value
+}
+// How evenly the active warps are spread over the four sub-partitions.  lo_spare: the fewest active warps on a
+// sub-partition that still has an idle warp (0xffffffff: none has).
+struct SmLoad {
+    uint32_t act[4], hi, lo, lo_spare;
+};
+__device__ __forceinline__ SmLoad sm_load(volatile SmCtl *c, uint32_t n_slots) {
+    SmLoad l;
+    l.hi = 0;
+    l.lo = l.lo_spare = 0xffffffffu;
+#pragma unroll
+    for (uint32_t sp = 0; sp < 4; sp++) {
+        const uint32_t cap = (n_slots + 3u - sp) >> 2;          // warps of the CTA on this sub-partition
+        const uint32_t v = sm_uniform(c->sp_active[sp]);
+        l.act[sp] = v;
+        if (cap) {
+            l.hi = v > l.hi ? v : l.hi;
+            l.lo = v < l.lo ? v : l.lo;
+            if (v < cap) l.lo_spare = v < l.lo_spare ? v : l.lo_spare;
+        }
+    }
+    return l;
+}
+// under the lock, after sp_active changed: a sub-partition is `over` when moving one of its units to an idle warp
+// elsewhere would leave both better off (two or more apart)
+__device__ __forceinline__ void sm_rebalance(volatile SmCtl *c, uint32_t n_slots) {
+    const SmLoad l = sm_load(c, n_slots);
+#pragma unroll
+    for (uint32_t sp = 0; sp < 4; sp++)
+        c->sp_over[sp] = (l.act[sp] == l.hi && l.lo_spare != 0xffffffffu && l.hi >= l.lo_spare + 2u) ? 1u : 0u;
+    c->uneven = (l.hi != l.lo && l.hi >= 2u) ? 1u : 0u;   // some warps share a sub-partition while others have more room
+}
+struct SmYield {
+    volatile SmCtl *c;
+    uint32_t sp, every, refills;
+    __device__ __forceinline__ bool want() {
+        refills++;
+        const uint32_t waiting = c->q_head != c->q_tail, over = c->sp_over[sp], turn = every && c->dry && c->uneven && refills >= every;
+        return sm_uniform(waiting | over | (turn ? 1u : 0u)) != 0u;
+    }
+};
+
+template <int kV>
+__global__ void __launch_bounds__(32 * kSmMaxSlots, 1) lzgpu_sm_kernel(const KArgs a, const SmArgs s) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    SmCtl *ctl = reinterpret_cast<SmCtl *>(sm_raw);
+    volatile SmCtl *vc = ctl;
+    // (the warp index through a shuffle: what derives from threadIdx counts as divergent, and every branch of the
+    // decoder below would get a convergence barrier)
+    const uint32_t w = sm_uniform(threadIdx.x >> 5), sp = w & 3u, cta = blockIdx.x, grid = gridDim.x;
+    // first wave: one unit of band w for the warps that have one (every thread computes the same counts)
+    // (bands of `grid` units in launch order, longest first; odd bands are dealt in reverse, so that the CTAs' sums agree)
+    uint32_t k0 = 0;
+    for (uint32_t i = 0; i < s.n_slots; i++) k0 += (i * grid + ((i & 1u) ? grid - 1u - cta : cta) < s.count) ? 1u : 0u;
+    {
+        vc->lock = 0;
+        vc->live = k0;
+        vc->dry = (uint64_t)grid * s.n_slots >= s.count ? 1u : 0u;
+        vc->q_head = vc->q_tail = 0;
+        for (uint32_t q = 0; q < 4; q++) {
+            uint32_t n = 0;
+            for (uint32_t i = q; i < k0; i += 4) n++;
+            vc->sp_active[q] = n;
+            vc->sp_over[q] = 0;
+        }
+        const uint32_t lo = k0 >> 2, hi = (k0 + 3u) >> 2;
+        vc->uneven = (lo != hi && hi >= 2u) ? 1u : 0u;
+    }
+    __syncthreads();
+
+    SmYield yield{vc, sp, s.rotate_every, 0};
+#ifdef LZGPU_SM_WATCHDOG
+    uint32_t idle_polls = 0;
+#endif
+    uint32_t idx = w * grid + ((w & 1u) ? grid - 1u - cta : cta), have = (w < s.n_slots && idx < s.count) ? 1u : 0u, fresh = 1, slot = w, last_slot = 0xffffffffu, patience = 0;
+    for (;;) {
+        if (!have) {
+            // idle: take a waiting unit if no sub-partition with an idle warp has fewer active warps than this one
+            // (not the unit this warp has just offered for exchange, unless nobody wanted it); leave when the CTA
+            // has nothing left.  The look is taken without the lock: idle warps must not keep it from the others.
+            uint32_t take = 0;
+            const uint32_t live = sm_uniform(vc->live);
+            if (sm_uniform(vc->q_head) != sm_uniform(vc->q_tail)) {
+                SmLoad l = sm_load(vc, s.n_slots);
+                if (l.act[sp] == l.lo_spare) {
+                    sm_lock(ctl);
+                    const uint32_t qh = sm_uniform(vc->q_head), qt = sm_uniform(vc->q_tail);
+                    l = sm_load(vc, s.n_slots);
+                    if (qh != qt && l.act[sp] == l.lo_spare) {
+                        const uint32_t head = sm_uniform(vc->ring[qh & 15u]);
+                        if (head != last_slot || patience == 0) {
+                            take = 1;
+                            slot = head;
+                            vc->q_head = qh + 1;
+                            vc->sp_active[sp] = l.act[sp] + 1;
+                            sm_rebalance(vc, s.n_slots);
+                        }
+                    }
+                    sm_unlock(ctl);
+                }
+            }
+            if (!take) {
+                if (live == 0) return;
+                if (patience) patience--;
+                __nanosleep(2000);
+#ifdef LZGPU_SM_WATCHDOG
+                if (++idle_polls > (uint32_t)LZGPU_SM_WATCHDOG * 500000u) asm volatile("trap;");
+#endif
+                continue;
+            }
+            have = 1;
+            fresh = 0;
+            last_slot = 0xffffffffu;
+        }
+        // ---- this warp decodes the unit in `slot`
+        for (;;) {
+            uint8_t *sb = sm_raw + kSmCtlBytes + (size_t)slot * s.slot_bytes;
+            uint16_t *P = reinterpret_cast<uint16_t *>(sb), *L = P + LZ_LAY(kV)::LIT;
+            SmSaved *sv = reinterpret_cast<SmSaved *>(sb + s.save_off);
+            UnitIO io;
+            io.stage = reinterpret_cast<uint8_t *>(P + a.stage_off);
+            io.inbuf = io.stage + 128;
+            Dec d;
+            WarpCopy wc;
+            const uint8_t *u_in;
+            uint8_t *u_out;
+            int32_t ui;
+            bool resume, run = true;
+            if (fresh) {
+                ui = a.order[a.slot0 + idx];
+                const lzgpu_unit u = a.units[ui];
+                io.in = a.in_base + u.in_off;
+                io.in_len = u.in_len;
+                io.out = a.out_base + u.out_off;
+                io.out_cap = u.out_cap;
+                io.progress = a.progress ? a.progress + ui : nullptr;
+                u_in = io.in;
+                u_out = io.out;
+                resume = false;
+                if (u.kind == LZGPU_KIND_LZMA2_GROUP) {
+                    run_unit_lzma2<kV>(u, io, P, L, a.lit_bits_cap, a.results[ui]);
+                    run = false;
+                } else {
+                    run = lzma1_start<kV>(u, io, P, L, d, wc);
+                    if (!run) lzma1_finish(d, u_in, u_out, a.results[ui]);
+                }
+            } else {
+                d = sv->d;
+                wc = sv->wc;
+                u_in = sv->in;
+                u_out = sv->out;
+                ui = sv->ui;
+                resume = true;
+            }
+            uint32_t next_slot = slot, keep = 1;
+            if (run) {
+                yield.refills = 0;
+                const int r = run_lzma<kV, SmYield>(d, wc, P, L, u_out, io.inbuf, yield, resume);
+                if (r == RUN_YIELD) {
+                    // hand the unit over: exchange it for one that waits, or leave it to an idle warp of a
+                    // sub-partition with room, or (exchange offer) leave it and wait for somebody else's
+                    sm_lock(ctl);
+                    const uint32_t qh = sm_uniform(vc->q_head), qt = sm_uniform(vc->q_tail), over = sm_uniform(vc->sp_over[sp]);
+                    const uint32_t offer = (yield.every && yield.refills >= yield.every && sm_uniform(vc->dry) && sm_uniform(vc->uneven)) ? 1u : 0u;
+                    if (qh != qt || over || offer) {
+                        sv->d = d;
+                        sv->wc = wc;
+                        sv->in = u_in;
+                        sv->out = u_out;
+                        sv->ui = ui;
+                        vc->ring[qt & 15u] = slot;
+                        vc->q_tail = qt + 1;
+                        if (qh != qt && !over) {          // exchange
+                            next_slot = sm_uniform(vc->ring[qh & 15u]);
+                            vc->q_head = qh + 1;
+                        } else {                          // leave it
+                            keep = 0;
+                            vc->sp_active[sp] = sm_uniform(vc->sp_active[sp]) - 1;
+                            sm_rebalance(vc, s.n_slots);
+                            last_slot = slot;
+                            patience = over ? 0u : 100u;
+                        }
+                    }
+                    sm_unlock(ctl);
+                    if (!keep) { have = 0; break; }
+                    if (next_slot == slot) {   // nobody to exchange with: carry on (state is still in registers)
+                        // (re-entering run_lzma needs the same d / wc: loop with fresh = 0 would reload them from sv,
+                        // which was not written; so store them)
+                        sv->d = d; sv->wc = wc; sv->in = u_in; sv->out = u_out; sv->ui = ui;
+                    }
+                    slot = next_slot;
+                    fresh = 0;
+                    continue;
+                }
+                lzma1_finish(d, u_in, u_out, a.results[ui]);
+            }
+            // ---- the unit is done: start the launch's next one in this slot, or retire
+            uint32_t nidx = 0xffffffffu;
+            if (!sm_uniform(vc->dry)) {
+                nidx = grid * s.n_slots + sm_fetch_global(s.next);
+                if (nidx >= s.count) nidx = 0xffffffffu;
+            }
+            if (nidx != 0xffffffffu) {
+                idx = nidx;
+                fresh = 1;
+                continue;
+            }
+            sm_lock(ctl);
+            vc->dry = 1;
+            vc->live = sm_uniform(vc->live) - 1;
+            vc->sp_active[sp] = sm_uniform(vc->sp_active[sp]) - 1;
+            sm_rebalance(vc, s.n_slots);
+            sm_unlock(ctl);
+            have = 0;
+            last_slot = 0xffffffffu;
+            patience = 0;
+            break;
+        }
+    }
+}
+
 // Tuning variant of the decoder (lzgpu_core.cuh, V_*): LZGPU_VARIANT in the environment
 // overrides the default; read once per plan.
 static int decoder_variant() {
@@ -303,6 +601,10 @@ struct DevState {
     // per-unit checksums of lzgpu_plan_crc32 / lzgpu_plan_crc64 (grow-only, for the same reason)
     uint8_t *d_sum = nullptr;
     uint64_t sum_cap = 0;
+    // literal tables of units with lc+lp > 4 (grow-only, for the same reason: a cudaFree per call was seen to take
+    // 0.1 - 0.8 s now and then)
+    uint8_t *d_litws = nullptr;
+    uint64_t litws_cap = 0;
 };
 
 struct lzgpu_ctx {
@@ -316,6 +618,7 @@ struct Launch {
     bool pb2;            // compact posState tables (every unit of the launch has pb <= 2)
     uint32_t slot0, count;
     size_t smem;
+    uint32_t sm_slots = 0, sm_grid = 0, sm_slot_bytes = 0;   // SM-resident scheduler geometry (0: one-warp CTAs)
 };
 
 struct lzgpu_plan {
@@ -333,6 +636,7 @@ struct lzgpu_plan {
     lzgpu_result *d_results = nullptr;
     uint16_t *d_lit_ws = nullptr;
     uint32_t *d_progress = nullptr;       // optional, set by the host-buffer entry point
+    uint32_t *d_next = nullptr;           // one unit counter per launch (SM-resident scheduler)
     uint64_t lit_ws_stride = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t last_stream = nullptr;
@@ -340,6 +644,7 @@ struct lzgpu_plan {
     bool borrowed = false;                // d_units / d_order / d_results live in the device's descriptor arena
     int variant = 0;
     int max_ctas_per_sm = 0;              // 0: as many as fit (14 at lc3 lp0 pb2)
+    uint32_t rotate_every = 16;           // SM-resident scheduler: refills between two exchange offers of a warp (LZGPU_ROTATE)
 };
 
 extern "C" int lzgpu_ctx_create(const int *devices, int n_devices, lzgpu_ctx **out) {
@@ -378,6 +683,7 @@ extern "C" void lzgpu_ctx_destroy(lzgpu_ctx *c) {
         if (d.h_tails) cudaFreeHost(d.h_tails);
         if (d.d_desc) cudaFree(d.d_desc);
         if (d.d_sum) cudaFree(d.d_sum);
+        if (d.d_litws) cudaFree(d.d_litws);
         if (d.d_in) cudaFree(d.d_in);
         if (d.d_out) cudaFree(d.d_out);
     }
@@ -390,11 +696,12 @@ extern "C" void lzgpu_plan_destroy(lzgpu_plan *p) {
     if (!p) return;
     cudaSetDevice(p->ctx->devs[p->dev_index].device);
     if (!p->borrowed) {
+        if (p->d_next) cudaFree(p->d_next);
         if (p->d_units) cudaFree(p->d_units);
         if (p->d_order) cudaFree(p->d_order);
         if (p->d_results) cudaFree(p->d_results);
     }
-    if (p->d_lit_ws) cudaFree(p->d_lit_ws);
+    if (p->d_lit_ws && !p->borrowed) cudaFree(p->d_lit_ws);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     delete p;
@@ -408,6 +715,7 @@ static size_t smem_bytes(uint32_t lit_bits, bool lit_global, bool pb2) {
     return sizeof(uint16_t) * probs_elems(lit_bits, lit_global, pb2) + 128 + kF2Stage;
 }
 
+static int ensure(uint8_t *&ptr, uint64_t &cap, uint64_t need);
 static int plan_create_impl(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *units, int64_t n,
                             uint64_t in_size, uint64_t out_size, lzgpu_plan **out, bool use_arena);
 extern "C" int lzgpu_plan_create(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *units, int64_t n,
@@ -425,6 +733,7 @@ static int plan_create_impl(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *uni
     p->dev_index = dev_index;
     p->variant = decoder_variant();
     if (const char *e = getenv("LZGPU_MAX_CTAS_PER_SM")) p->max_ctas_per_sm = atoi(e);
+    if (const char *e = getenv("LZGPU_ROTATE")) p->rotate_every = (uint32_t)atoi(e);
     p->n = n;
     p->in_size = in_size;
     p->out_size = out_size;
@@ -490,6 +799,31 @@ static int plan_create_impl(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *uni
         }
         s = e;
     }
+    // SM-resident scheduler (lzgpu_sm_kernel) for the launches of the default decoder whose tables live in shared memory:
+    // one CTA per SM, `sm_slots` units resident per CTA.  LZGPU_SCHED=0 keeps the one-warp CTAs.
+    {
+        const bool sched_on = !(getenv("LZGPU_SCHED") && atoi(getenv("LZGPU_SCHED")) == 0);
+        int nsm = 0;
+        if (sched_on && p->variant == 33 && cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->devs[dev_index].device) == cudaSuccess && nsm > 0) {
+            bool any = false;
+            for (size_t li = 0; li < p->launches.size() && li < 64; li++) {
+                Launch &L = p->launches[li];
+                if (L.lit_global || L.count == 0) continue;
+                const uint32_t slot_bytes = (uint32_t)((L.smem + 15u) & ~(size_t)15u) + kSmSaveBytes;
+                uint32_t smax = std::min<uint32_t>(kSmMaxSlots, (232448u - kSmCtlBytes) / slot_bytes);
+                if (p->max_ctas_per_sm > 0) smax = std::min<uint32_t>(smax, (uint32_t)p->max_ctas_per_sm);
+                if (smax == 0) continue;
+                L.sm_grid = std::min<uint32_t>((uint32_t)nsm, L.count);
+                L.sm_slots = std::min<uint32_t>(smax, (L.count + L.sm_grid - 1) / L.sm_grid);
+                L.sm_slot_bytes = slot_bytes;
+                any = true;
+            }
+            if (any) {
+                cudaFuncSetAttribute(lzgpu_sm_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+                cudaFuncSetAttribute(lzgpu_sm_kernel<33 | V_PB2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+            }
+        }
+    }
     auto bail = [&](cudaError_t e, const char *what) {
         std::string m = std::string(what) + ": " + cudaGetErrorString(e);
         lzgpu_plan_destroy(p);
@@ -498,7 +832,7 @@ static int plan_create_impl(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *uni
     cudaError_t e;
     if (n > 0 && use_arena) {
         DevState &ds = ctx->devs[dev_index];
-        const uint64_t need = (sizeof(lzgpu_unit) + sizeof(lzgpu_result) + sizeof(int32_t)) * (uint64_t)n + 512;
+        const uint64_t need = (sizeof(lzgpu_unit) + sizeof(lzgpu_result) + sizeof(int32_t)) * (uint64_t)n + 256 + 512;
         if (ds.desc_cap < need) {
             if (ds.d_desc) cudaFree(ds.d_desc);
             ds.d_desc = nullptr; ds.desc_cap = 0;
@@ -510,12 +844,14 @@ static int plan_create_impl(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *uni
         p->d_units = reinterpret_cast<lzgpu_unit *>(ds.d_desc);
         p->d_results = reinterpret_cast<lzgpu_result *>(ds.d_desc + sizeof(lzgpu_unit) * (size_t)n);
         p->d_order = reinterpret_cast<int32_t *>(ds.d_desc + (sizeof(lzgpu_unit) + sizeof(lzgpu_result)) * (size_t)n);
+        p->d_next = reinterpret_cast<uint32_t *>(ds.d_desc + (sizeof(lzgpu_unit) + sizeof(lzgpu_result) + sizeof(int32_t)) * (size_t)n);   // 64 counters
     }
     if (n > 0) {
         if (!use_arena) {
         if ((e = cudaMalloc(&p->d_units, sizeof(lzgpu_unit) * (size_t)n)) != cudaSuccess) return bail(e, "cudaMalloc units");
         if ((e = cudaMalloc(&p->d_results, sizeof(lzgpu_result) * (size_t)n)) != cudaSuccess) return bail(e, "cudaMalloc results");
         if ((e = cudaMalloc(&p->d_order, sizeof(int32_t) * std::max<size_t>(1, runnable.size()))) != cudaSuccess) return bail(e, "cudaMalloc order");
+        if ((e = cudaMalloc(&p->d_next, sizeof(uint32_t) * 64)) != cudaSuccess) return bail(e, "cudaMalloc counters");
         }
         if ((e = cudaMemcpy(p->d_units, p->units.data(), sizeof(lzgpu_unit) * (size_t)n, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload units");
         if (!runnable.empty() && (e = cudaMemcpy(p->d_order, runnable.data(), sizeof(int32_t) * runnable.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload order");
@@ -523,7 +859,11 @@ static int plan_create_impl(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *uni
     }
     if (ws_slots) {
         p->lit_ws_stride = (uint64_t)0x300 << ws_bits;
-        if ((e = cudaMalloc(&p->d_lit_ws, ws_slots * p->lit_ws_stride * 2)) != cudaSuccess) return bail(e, "cudaMalloc literal workspace");
+        if (use_arena) {
+            DevState &ds = ctx->devs[dev_index];
+            if (ensure(ds.d_litws, ds.litws_cap, ws_slots * p->lit_ws_stride * 2)) return bail(cudaErrorMemoryAllocation, "cudaMalloc literal workspace");
+            p->d_lit_ws = reinterpret_cast<uint16_t *>(ds.d_litws);
+        } else if ((e = cudaMalloc(&p->d_lit_ws, ws_slots * p->lit_ws_stride * 2)) != cudaSuccess) return bail(e, "cudaMalloc literal workspace");
     }
     if ((e = cudaEventCreate(&p->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&p->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
@@ -577,7 +917,20 @@ extern "C" int lzgpu_plan_launch(lzgpu_plan *p, const uint8_t *d_in, uint8_t *d_
             const size_t want = ((233472u / (unsigned)p->max_ctas_per_sm) - 1024u) & ~(size_t)15;
             if (want > smem && want <= 48u * 1024u) smem = want;
         }
-        if (L.lit_global) launch_decode<true>(p->variant, false, L.count, smem, ls, a);
+        const size_t li = (size_t)(&L - p->launches.data());
+        if (L.sm_slots && p->d_next) {
+            SmArgs sa;
+            sa.count = L.count;
+            sa.n_slots = L.sm_slots;
+            sa.slot_bytes = L.sm_slot_bytes;
+            sa.save_off = L.sm_slot_bytes - kSmSaveBytes;
+            sa.rotate_every = p->rotate_every;
+            sa.next = p->d_next + li;
+            CUDA_TRY(cudaMemsetAsync(sa.next, 0, sizeof(uint32_t), ls));
+            const size_t sm_bytes = kSmCtlBytes + (size_t)L.sm_slots * L.sm_slot_bytes;
+            if (L.pb2) lzgpu_sm_kernel<33 | V_PB2><<<L.sm_grid, 32 * L.sm_slots, sm_bytes, ls>>>(a, sa);
+            else lzgpu_sm_kernel<33><<<L.sm_grid, 32 * L.sm_slots, sm_bytes, ls>>>(a, sa);
+        } else if (L.lit_global) launch_decode<true>(p->variant, false, L.count, smem, ls, a);
         else launch_decode<false>(p->variant, L.pb2, L.count, smem, ls, a);
         CUDA_TRY(cudaGetLastError());
     }

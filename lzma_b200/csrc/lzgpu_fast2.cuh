@@ -36,7 +36,7 @@ namespace lzgpu {
 //   %4 the block's result, %5.. its inputs.
 #define F2_REGS                                                                         \
     ".reg .pred one, nz, q0, q1, mbp, ne;\n\t"                                          \
-    ".reg .b32 t, tn, u3, bd, k, pn, p, pz, lo, hi, ya, yb, yc, nS;\n\t"
+    ".reg .b32 t, t2, tn, u3, bd, k, pn, p, pz, lo, hi, ya, yb, yc, nS;\n\t"
 
 // range >> 11 of the NEXT step is selected from the two shifts of the un-normalised range (>> 3 if the
 // normalisation will shift it left by 8, else >> 11) as soon as that range exists, instead of being taken
@@ -58,6 +58,18 @@ namespace lzgpu {
 #define F2_TSEL ""
 #endif
 
+// code -= bound for a decoded 1, as  code = min(code, code - bound)  in unsigned arithmetic (code < bound: the difference
+// wraps above 2^31 > code): ptxas fuses the pair into ONE add-min instruction (VIADDMNMX) that does not wait for the
+// bit's predicate, where the predicated subtraction pays the 13-cycle guard latency.
+#ifndef F2_CMIN
+#define F2_CMIN 1
+#endif
+#if F2_CMIN
+#define F2_CSUB(Q) "sub.u32 t2, %1, bd;\n\tmin.u32 %1, %1, t2;\n\t"
+#else
+#define F2_CSUB(Q) "@" Q " sub.u32 %1, %1, bd;\n\t"
+#endif
+
 // DecodeBit (range_decoder.go:57-98) on probability register P, predicate Q = the bit, followed by the
 // normalisation: consume the byte in hand, fetch the one after it.  Ordered along the critical path.
 // (The input address is advanced BEFORE the load: an add placed after it would have to wait until the
@@ -71,7 +83,7 @@ namespace lzgpu {
     "selp.b32 %0, t, bd, " Q ";\n\t"                                                    \
     "setp.lt.u32 nz, %0, 0x1000000;\n\t"                                                \
     F2_TAHEAD                                                                           \
-    "@" Q " sub.u32 %1, %1, bd;\n\t"                                                    \
+    F2_CSUB(Q)                                                                          \
     F2_TSEL                                                                             \
     "@nz shl.b32 %0, %0, 8;\n\t"                                                        \
     "@nz add.u32 %3, %3, 1;\n\t"                                                        \
@@ -103,7 +115,7 @@ namespace lzgpu {
     F2_TAHEAD                                                                           \
     "selp.b32 " PN ", hi, lo, " QC ";\n\t"                                              \
     F2_TSEL                                                                             \
-    "@" QC " sub.u32 %1, %1, bd;\n\t"                                                   \
+    F2_CSUB(QC)                                                                         \
     "@" QC " add.u32 " YN ", " YN ", 4;\n\t"                                            \
     "@nz shl.b32 %0, %0, 8;\n\t"                                                        \
     "@nz add.u32 %3, %3, 1;\n\t"                                                        \
@@ -338,7 +350,43 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
                  "ld.shared.u8 %2, [%3];"                                               \
                  : F2_IO(d) : : "memory")
 
-// eight equiprobable bits between two normalisations: thresholds R >> 1 .. R >> 8, result MSB first
+// eight equiprobable bits between two normalisations: thresholds R >> 1 .. R >> 8, result MSB first.
+// A step is  code = min(code, code - (R >> j))  in unsigned arithmetic: when code < R >> j the difference wraps to more
+// than 2^31 > code, so the minimum keeps code (R >> j < 2^31).  The serial chain per bit is SUB -> MIN (10 cycles); the
+// predicated form (setp -> @p sub) pays the 13-cycle guard latency in every step (18 cycles, profiles/r02_ubench.txt).
+// The bits are read off afterwards (a step that changed code decided 1), outside the chain.
+#ifndef F2_DMIN
+#define F2_DMIN 1
+#endif
+#if F2_DMIN
+#define F2_DSTEP(J, M, CI, CO)                                                          \
+    "shr.u32 rj, %2, " J ";\n\t"                                                        \
+    "sub.u32 tj, " CI ", rj;\n\t"                                                       \
+    "min.u32 " CO ", " CI ", tj;\n\t"                                                   \
+    "setp.ne.u32 one, " CO ", " CI ";\n\t"                                              \
+    "@one or.b32 %1, %1, " M ";\n\t"
+#define F2_DIRECT8(CODE, ACC, R)                                                        \
+    asm("{\n\t.reg .pred one;\n\t.reg .b32 rj, tj, c<8>;\n\tmov.u32 %1, 0;\n\t"         \
+        F2_DSTEP("1", "128", "%0", "c1") F2_DSTEP("2", "64", "c1", "c2") F2_DSTEP("3", "32", "c2", "c3") \
+        F2_DSTEP("4", "16", "c3", "c4") F2_DSTEP("5", "8", "c4", "c5") F2_DSTEP("6", "4", "c5", "c6") \
+        F2_DSTEP("7", "2", "c6", "c7") F2_DSTEP("8", "1", "c7", "%0") "}"                \
+        : "+r"(CODE), "=&r"(ACC) : "r"(R))
+// the first K (< 8) of those steps only: a dead step subtracts 0
+#define F2_DSTEP_IF(J, M, CI, CO)                                                       \
+    "setp.le.u32 live, " J ", %3;\n\t"                                                  \
+    "shr.u32 rj, %2, " J ";\n\t"                                                        \
+    "selp.b32 rj, rj, 0, live;\n\t"                                                     \
+    "sub.u32 tj, " CI ", rj;\n\t"                                                       \
+    "min.u32 " CO ", " CI ", tj;\n\t"                                                   \
+    "setp.ne.u32 one, " CO ", " CI ";\n\t"                                              \
+    "@one or.b32 %1, %1, " M ";\n\t"
+#define F2_DIRECT_PART(CODE, ACC, R, K)                                                 \
+    asm("{\n\t.reg .pred one, live;\n\t.reg .b32 rj, tj, c<8>;\n\tmov.u32 %1, 0;\n\t"   \
+        F2_DSTEP("1", "128", "%0", "c1") F2_DSTEP_IF("2", "64", "c1", "c2") F2_DSTEP_IF("3", "32", "c2", "c3") \
+        F2_DSTEP_IF("4", "16", "c3", "c4") F2_DSTEP_IF("5", "8", "c4", "c5") F2_DSTEP_IF("6", "4", "c5", "c6") \
+        F2_DSTEP_IF("7", "2", "c6", "%0") "}"                                           \
+        : "+r"(CODE), "=&r"(ACC) : "r"(R), "r"(K))
+#else
 #define F2_DSTEP(J, M)                                                                  \
     "shr.u32 rj, %2, " J ";\n\t"                                                        \
     "setp.ge.u32 one, %0, rj;\n\t"                                                      \
@@ -361,6 +409,7 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
         F2_DSTEP("1", "128") F2_DSTEP_IF("2", "64") F2_DSTEP_IF("3", "32") F2_DSTEP_IF("4", "16") \
         F2_DSTEP_IF("5", "8") F2_DSTEP_IF("6", "4") F2_DSTEP_IF("7", "2") "}"             \
         : "+r"(CODE), "=&r"(ACC) : "r"(R), "r"(K))
+#endif
 
 #define F2_FAIL(ST, SITE) do { d.status = (ST); d.site = (SITE); return OP_DONE; } while (0)
 

@@ -276,9 +276,19 @@ LZ_DEV void f2_leave(Dec &d) {
 // Decode symbols until the range-coded part ends (Reader1.Read driving
 // decompress(), reader1.go:223-254).  On return d.status / d.site are set and no
 // store is pending.
-template <int kV>
-LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8_t *dict_base, uint8_t *inbuf = nullptr) {
-    bool fast = false;   // which decoder runs (lzgpu_core.cuh, kFast)
+// Time slicing (the SM-resident scheduler of lzgpu.cu): a unit may be taken off its warp where the fast decoder refills
+// its input stage -- the one point of the symbol loop where everything that is live sits in Dec / WarpCopy and in the
+// unit's own shared memory.  run_lzma then returns RUN_YIELD; called again with resume = true (by any warp of the CTA, on
+// the same Dec / WarpCopy contents) it carries on with that refill.
+enum : int { RUN_DONE = 0, RUN_YIELD = 1 };
+struct NoYield {
+    LZ_DEV bool want() { return false; }
+};
+
+template <int kV, class Yield = NoYield>
+LZ_DEV int run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8_t *dict_base, uint8_t *inbuf, Yield &yield,
+                    bool resume = false) {
+    bool fast = resume;   // which decoder runs (lzgpu_core.cuh, kFast)
     set_fast_limits(d);
     d.stage = wc.stage;
     for (;;) {
@@ -286,10 +296,18 @@ LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8
         if (kV & V_CHAIN) {
             for (;;) {
                 if (fast) {
-                    op = decode_fast2<kV>(d, wc, len, dist);
-                    if (op != OP_SWITCH) break;
-                    // stage used up (refill) or the unit's tail reached (careful decoder from here on)
-                    publish_progress(d, wc);
+                    if (!resume) {
+                        op = decode_fast2<kV>(d, wc, len, dist);
+                        if (op != OP_SWITCH) break;
+                        // stage used up (refill) or the unit's tail reached (careful decoder from here on)
+                        publish_progress(d, wc);
+                        if (yield.want()) {
+                            LZ_CP_WAIT();   // window-copy sources this warp's cp.async is still fetching into the copy stage
+                            LZ_SYNC();
+                            return RUN_YIELD;
+                        }
+                    }
+                    resume = false;
                     if (d.outp <= d.fast_out_end && f2_enter<kV>(d, d.g0 + (d.ips - d.sIn), inbuf)) continue;
                     f2_leave(d);
                     fast = false;
@@ -414,6 +432,12 @@ LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8
     if (kV & V_CHAIN) { if (fast) f2_leave(d); }
     else if (fast) d.ip -= 4;   // the word loaded ahead was never consumed
     wc_commit(wc);
+    return RUN_DONE;
+}
+template <int kV>
+LZ_DEV void run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8_t *dict_base, uint8_t *inbuf = nullptr) {
+    NoYield ny;
+    run_lzma<kV, NoYield>(d, wc, P, L, dict_base, inbuf, ny, false);
 }
 
 template <int kV>
@@ -434,12 +458,10 @@ struct UnitIO {
     uint32_t *progress;      // host-mapped progress counter of this unit (streamed D2H), or null
 };
 
-// LZMA1 unit (kind RAW; ALONE units are converted by the host).
+// LZMA1 unit (kind RAW; ALONE units are converted by the host): set-up, symbol loop, verdict.  The three are separate so
+// that the SM-resident scheduler can run the loop in time slices.
 template <int kV>
-LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, uint16_t *L,
-                           lzgpu_result &res) {
-    Dec d;
-    WarpCopy wc;
+LZ_DEV bool lzma1_start(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, uint16_t *L, Dec &d, WarpCopy &wc) {
     wc.pend_len = 0;
     wc.pend_dst = io.out;
     wc.pend_staged = 0;
@@ -468,21 +490,30 @@ LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     d.in_end = io.in + io.in_len;
     d.status = LZGPU_OK;
     d.site = 0;
+    d.nextw = 0;
     coder_reset<kV>(d, P, L, (uint32_t)u.lc + u.lp);
 
-    int32_t r = 0;
-    r = rc_init(d);
-    if (r < 0) { d.status = LZGPU_UNEXPECTED_EOF; }                       // "rangeDec.Init: %w" of io.EOF
-    else if (r > 0) { d.status = LZGPU_RESULT_ERROR; d.site = LZGPU_SITE_RC_INIT; }
-    else run_lzma<kV>(d, wc, P, L, io.out, io.inbuf);
-
+    const int32_t r = rc_init(d);
+    if (r < 0) { d.status = LZGPU_UNEXPECTED_EOF; return false; }        // "rangeDec.Init: %w" of io.EOF
+    if (r > 0) { d.status = LZGPU_RESULT_ERROR; d.site = LZGPU_SITE_RC_INIT; return false; }
+    return true;
+}
+LZ_DEV void lzma1_finish(const Dec &d, const uint8_t *in, const uint8_t *out, lzgpu_result &res) {
     LZ_IF_LANE0_ONLY {
         res.status = d.status;
         res.err_site = d.site;
-        res.bytes_out = (uint64_t)(d.outp - io.out);
-        res.bytes_in = rc_consumed(d, io.in);
+        res.bytes_out = (uint64_t)(d.outp - out);
+        res.bytes_in = rc_consumed(d, in);
         res.final_code = d.code;
     }
+}
+template <int kV>
+LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, uint16_t *L,
+                           lzgpu_result &res) {
+    Dec d;
+    WarpCopy wc;
+    if (lzma1_start<kV>(u, io, P, L, d, wc)) run_lzma<kV>(d, wc, P, L, io.out, io.inbuf);
+    lzma1_finish(d, io.in, io.out, res);
 }
 
 // LZMA2 group: walk the chunks (Reader2.startChunk + Read, reader2.go:100-250).

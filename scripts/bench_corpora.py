@@ -182,6 +182,11 @@ if __name__ == "__main__":
         if "--config5" in sys.argv:        # 16 384 x 4 MiB on one GPU (64 GiB of output in HBM)
             run_replicated(ctx, 16384, 4 << 20)
             sys.exit(0)
+        if "--shapes" in sys.argv:         # e.g. --shapes text:148,text:1024:4,random:148   (kind:units[:MiB per unit])
+            for spec in sys.argv[sys.argv.index("--shapes") + 1].split(","):
+                f = spec.split(":")
+                run(ctx, f[0], int(f[1]), (int(f[2]) if len(f) > 2 else 1) << 20)
+            sys.exit(0)
         if "--quick-random" in sys.argv:   # incompressible data: 9 adaptive bits per byte, literals only
             run(ctx, "random", 148, 1 << 20)
             run(ctx, "mixed", 1024, 1 << 20)

@@ -517,3 +517,95 @@ def test_long_and_overlapping_matches(ctx):
     for (name, s, cap), g in zip(cs, got):
         same_outcome(O.lzma_alone(s, cap), g.status, g.err_site, g.data, name)
         assert g.data == d
+
+
+def _hetero_streams(n_distinct):
+    """Streams of very different lengths and compressibility (text, noise, mixed; 24 KiB ... 320 KiB): what makes units
+    of one SM finish at different times."""
+    plains = []
+    for i in range(n_distinct):
+        size = (24 + 37 * (i % 9)) << 10
+        kind = (K.text_block, K.random_block, K.mixed_block)[i % 3]
+        plains.append(kind(7000 + i, size))
+    return plains, [K.compress_alone(p, size_mode=("eos", "eos+size")[i % 2]) for i, p in enumerate(plains)]
+
+
+@pytest.mark.parametrize("n_units,rotate", [(2072, "1"), (2500, "3"), (5000, "16"), (700, "2")])
+def test_sm_scheduler_time_slicing(n_units, rotate, monkeypatch):
+    """The SM-resident scheduler (lzgpu_sm_kernel): up to 14 units per CTA, units exchanged between warps at every
+    `rotate`-th refill of the input stage, units handed to idle warps when others finish, later waves started from
+    the global counter.  Every unit's bytes must be those of the plaintext, whatever warp decoded which part, and
+    equal to what the one-warp CTAs (LZGPU_SCHED=0) produce."""
+    plains, streams = _hetero_streams(27)
+    pick = [(k * 7 + k // 27) % 27 for k in range(n_units)]
+    crcs = [zlib.crc32(p) for p in plains]
+    outs = {}
+    for sched in ("1", "0"):
+        monkeypatch.setenv("LZGPU_SCHED", sched)
+        monkeypatch.setenv("LZGPU_ROTATE", rotate)
+        with B.Context([0]) as c:
+            got = B.decode_alone_streams(c, [streams[i] for i in pick], [len(plains[i]) for i in pick])
+        for k, (i, g) in enumerate(zip(pick, got)):
+            assert g.status == L.OK and len(g.data) == len(plains[i]) and zlib.crc32(g.data) == crcs[i], (sched, k, i, g.status, g.err_site)
+        outs[sched] = [(g.status, g.err_site, g.bytes_in) for g in got]
+    assert outs["1"] == outs["0"]
+
+
+def test_sm_scheduler_with_bad_units_and_lzma2(monkeypatch):
+    """Corrupt LZMA1 units (they end early: their warps go idle and take over others' units) and LZMA2 groups (not
+    time-sliced) next to sliced LZMA1 units in the same CTAs, in ONE call."""
+    monkeypatch.setenv("LZGPU_ROTATE", "1")
+    plains, streams = _hetero_streams(12)
+    l2_blocks = [K.text_block(4242 + i, (40 + 30 * i) << 10) for i in range(4)]
+    l2 = K.lzma2_with_resets(l2_blocks, dict_size=1 << 20)
+    l2_plain = b"".join(l2_blocks)
+    l2_units, l2_total, sst = B.scan_lzma2(l2, 1 << 20)
+    assert sst == L.OK and l2_total == len(l2_plain) and len(l2_units) == 4
+    n_alone, n_l2 = 1500, 120
+    blobs, units, layout, off, out_off = [], [], [], 0, 0
+    for k in range(n_alone):
+        i = k % 12
+        sb = bytearray(streams[i])
+        if k % 5 == 0:
+            sb[13 + 40 + (k % 97)] ^= 0x5A      # damage inside the range-coded part
+        sb = bytes(sb)
+        st, u = B.parse_alone_header(sb)
+        u.kind = L.KIND_LZMA1_ALONE
+        u.in_off, u.in_len, u.out_off, u.out_cap = off, len(sb), out_off, len(plains[i])
+        units.append(u)
+        layout.append((sb, len(plains[i])))
+        blobs.append(sb + bytes(-len(sb) % 16))
+        off += len(blobs[-1])
+        out_off += (len(plains[i]) + 31) & ~15
+        if k % (n_alone // n_l2) == 0:            # an LZMA2 stream's groups in between
+            for t in l2_units:
+                u2 = L.Unit()
+                C.memmove(C.byref(u2), C.byref(t), C.sizeof(L.Unit))
+                u2.in_off += off
+                u2.out_off += out_off
+                units.append(u2)
+                layout.append(None)
+            blobs.append(l2 + bytes(-len(l2) % 16))
+            off += len(blobs[-1])
+            out_off += (l2_total + 31) & ~15
+    in_buf = np.frombuffer(b"".join(blobs) + bytes(16), dtype=np.uint8)
+    out_buf = np.zeros(out_off + 16, dtype=np.uint8)
+    with B.Context([0]) as c:
+        res, st = c.decode_batch(units, in_buf, out_buf)
+    k, n_bad = 0, 0
+    while k < len(units):
+        if layout[k] is not None:
+            sb, cap = layout[k]
+            r, u = res[k], units[k]
+            want = O.lzma_alone(sb, cap)
+            n_bad += r.status != L.OK
+            same_outcome(want, r.status, r.err_site, out_buf[u.out_off:u.out_off + r.bytes_out].tobytes(), f"unit {k}")
+            k += 1
+        else:
+            got = b""
+            for j in range(4):
+                assert res[k + j].status == L.OK, (k, j, res[k + j].status, res[k + j].err_site)
+                got += out_buf[units[k + j].out_off:units[k + j].out_off + res[k + j].bytes_out].tobytes()
+            assert got == l2_plain
+            k += 4
+    assert n_bad > 100
