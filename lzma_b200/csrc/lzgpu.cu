@@ -90,7 +90,8 @@ struct SmArgs {
     uint32_t n_slots;        // units resident per CTA = warps per CTA
     uint32_t slot_bytes;     // shared memory of one slot: tables, stages, save area
     uint32_t save_off;       // offset of the save area inside a slot
-    uint32_t rotate_every;   // refills between two exchange offers of a warp (0: never)
+    uint32_t rotate_every;   // refills between two looks of a warp for a unit to exchange its own with (0: never)
+    uint32_t rotate_mode;    // 0: exchange with a unit that has less work left and sits on a less crowded sub-partition; 1: with anybody
     uint32_t *next;          // units started beyond the first wave (device counter, zeroed before the launch)
 };
 struct SmCtl {
@@ -102,6 +103,9 @@ struct SmCtl {
     uint32_t sp_over[4];     // that sub-partition has more active warps than its share while another has room
     uint32_t uneven;         // the active warps are not spread evenly: exchanging units pays
     uint32_t ring[16];
+    uint32_t rem[16];        // per slot: compressed bytes its unit has left (0xffffffff: a unit that is not sliced)
+    uint32_t where[16];      // per slot: sub-partition of the warp decoding it (4: waiting in the ring / empty)
+    uint32_t origin[16];     // per slot waiting in the ring: sub-partition of the warp that put it there
 };
 struct SmSaved {
     Dec d;
@@ -110,7 +114,7 @@ struct SmSaved {
     uint8_t *out;
     int32_t ui;
 };
-constexpr uint32_t kSmCtlBytes = 128;
+constexpr uint32_t kSmCtlBytes = 320;   // >= sizeof(SmCtl), multiple of 16
 constexpr uint32_t kSmSaveBytes = (sizeof(SmSaved) + 15u) & ~15u;
 constexpr uint32_t kSmMaxSlots = 14;
 static_assert(sizeof(SmCtl) <= kSmCtlBytes, "SmCtl");
@@ -177,13 +181,47 @@ __device__ __forceinline__ void sm_rebalance(volatile SmCtl *c, uint32_t n_slots
         c->sp_over[sp] = (l.act[sp] == l.hi && l.lo_spare != 0xffffffffu && l.hi >= l.lo_spare + 2u) ? 1u : 0u;
     c->uneven = (l.hi != l.lo && l.hi >= 2u) ? 1u : 0u;   // some warps share a sub-partition while others have more room
 }
+// Would a warp of sub-partition `sp`, decoding a unit with `rem` compressed bytes left, do well to exchange it for the
+// unit at the head of the ring?  Yes when that puts the unit with MORE left on the LESS crowded sub-partition (the
+// warp that offered the head unit is idle: its sub-partition counts one more when it takes a unit again).  Units on a
+// crowded sub-partition fall behind, so between equal units the same rule is a rotation that keeps them level; between
+// unequal ones it lets the long ones run where fewer warps share the issue slots, and the SM drains later.
+// mode 1: always (plain rotation).
+__device__ __forceinline__ uint32_t sm_accept(volatile SmCtl *c, uint32_t sp, uint32_t rem, uint32_t mode) {
+    const uint32_t qh = c->q_head;
+    if (qh == c->q_tail) return 0u;
+    if (mode == 1u) return 1u;
+    const uint32_t h = c->ring[qh & 15u], ca = c->sp_active[c->origin[h] & 3u] + 1u, cb = c->sp_active[sp], ra = c->rem[h];
+    return ((ca > cb && ra > rem) || (ca < cb && ra < rem)) ? 1u : 0u;
+}
+// Asked at every refill of the fast decoder's input stage: should this unit leave its warp?
+//   1  a unit waits in the ring and exchanging this one for it is a gain (sm_accept);
+//   2  this sub-partition holds more active warps than its share and another has an idle warp: leave it to that one;
+//   3  (every `every` refills, when no unit of the launch is left to start) some unit on a less crowded sub-partition
+//      has less left than this one: put this one into the ring and wait for one of those warps to come by.
 struct SmYield {
     volatile SmCtl *c;
-    uint32_t sp, every, refills;
-    __device__ __forceinline__ bool want() {
+    uint32_t sp, every, mode, n_slots, slot, refills, intent, rem;
+    __device__ __forceinline__ bool want(const Dec &d) {
         refills++;
-        const uint32_t waiting = c->q_head != c->q_tail, over = c->sp_over[sp], turn = every && c->dry && c->uneven && refills >= every;
-        return sm_uniform(waiting | over | (turn ? 1u : 0u)) != 0u;
+        rem = (uint32_t)(d.in_end - (d.g0 + (d.ips - d.sIn)));
+        c->rem[slot] = rem;
+        uint32_t it = 0;
+        if (sm_accept(c, sp, rem, mode)) it = 1;
+        else if (c->sp_over[sp]) it = 2;
+        else if (every && refills >= every && c->dry && c->uneven) {
+            refills = 0;
+            if (mode == 1u) it = 3;
+            else {
+                const uint32_t mine = c->sp_active[sp];
+                for (uint32_t u = 0; u < n_slots; u++) {
+                    const uint32_t wu = c->where[u], ru = c->rem[u];
+                    if (wu < 4u && c->sp_active[wu] < mine && ru != 0xffffffffu && ru + 1024u < rem) it = 3;
+                }
+            }
+        }
+        intent = sm_uniform(it);
+        return intent != 0u;
     }
 };
 
@@ -212,10 +250,15 @@ __global__ void __launch_bounds__(32 * kSmMaxSlots, 1) lzgpu_sm_kernel(const KAr
         }
         const uint32_t lo = k0 >> 2, hi = (k0 + 3u) >> 2;
         vc->uneven = (lo != hi && hi >= 2u) ? 1u : 0u;
+        for (uint32_t i = 0; i < 16; i++) {
+            vc->rem[i] = 0xffffffffu;
+            vc->where[i] = i < k0 ? (i & 3u) : 4u;
+            vc->origin[i] = 0;
+        }
     }
     __syncthreads();
 
-    SmYield yield{vc, sp, s.rotate_every, 0};
+    SmYield yield{vc, sp, s.rotate_every, s.rotate_mode, s.n_slots, 0, 0, 0, 0};
 #ifdef LZGPU_SM_WATCHDOG
     uint32_t idle_polls = 0;
 #endif
@@ -240,6 +283,7 @@ __global__ void __launch_bounds__(32 * kSmMaxSlots, 1) lzgpu_sm_kernel(const KAr
                             slot = head;
                             vc->q_head = qh + 1;
                             vc->sp_active[sp] = l.act[sp] + 1;
+                            vc->where[head] = sp;
                             sm_rebalance(vc, s.n_slots);
                         }
                     }
@@ -284,10 +328,13 @@ __global__ void __launch_bounds__(32 * kSmMaxSlots, 1) lzgpu_sm_kernel(const KAr
                 u_in = io.in;
                 u_out = io.out;
                 resume = false;
+                vc->where[slot] = sp;
                 if (u.kind == LZGPU_KIND_LZMA2_GROUP) {
+                    vc->rem[slot] = 0xffffffffu;
                     run_unit_lzma2<kV>(u, io, P, L, a.lit_bits_cap, a.results[ui]);
                     run = false;
                 } else {
+                    vc->rem[slot] = u.in_len > 0xfffffffeull ? 0xfffffffeu : (uint32_t)u.in_len;
                     run = lzma1_start<kV>(u, io, P, L, d, wc);
                     if (!run) lzma1_finish(d, u_in, u_out, a.results[ui]);
                 }
@@ -299,17 +346,22 @@ __global__ void __launch_bounds__(32 * kSmMaxSlots, 1) lzgpu_sm_kernel(const KAr
                 ui = sv->ui;
                 resume = true;
             }
-            uint32_t next_slot = slot, keep = 1;
             if (run) {
                 yield.refills = 0;
-                const int r = run_lzma<kV, SmYield>(d, wc, P, L, u_out, io.inbuf, yield, resume);
-                if (r == RUN_YIELD) {
-                    // hand the unit over: exchange it for one that waits, or leave it to an idle warp of a
-                    // sub-partition with room, or (exchange offer) leave it and wait for somebody else's
+                int r;
+                uint32_t action = 0;   // 1: carry on with the unit in `slot` (another one after an exchange), 2: idle
+                for (;;) {
+                    yield.slot = slot;
+                    r = run_lzma<kV, SmYield>(d, wc, P, L, u_out, io.inbuf, yield, resume);
+                    if (r != RUN_YIELD) break;
+                    resume = true;
                     sm_lock(ctl);
                     const uint32_t qh = sm_uniform(vc->q_head), qt = sm_uniform(vc->q_tail), over = sm_uniform(vc->sp_over[sp]);
-                    const uint32_t offer = (yield.every && yield.refills >= yield.every && sm_uniform(vc->dry) && sm_uniform(vc->uneven)) ? 1u : 0u;
-                    if (qh != qt || over || offer) {
+                    uint32_t give = 0;                     // 1: exchange, 2: leave to an idle warp, 3: offer
+                    if (sm_uniform(sm_accept(vc, sp, yield.rem, s.rotate_mode))) give = 1;
+                    else if (over) give = 2;
+                    else if (yield.intent == 3 && sm_uniform(vc->dry) && sm_uniform(vc->uneven)) give = 3;
+                    if (give) {
                         sv->d = d;
                         sv->wc = wc;
                         sv->in = u_in;
@@ -317,28 +369,27 @@ __global__ void __launch_bounds__(32 * kSmMaxSlots, 1) lzgpu_sm_kernel(const KAr
                         sv->ui = ui;
                         vc->ring[qt & 15u] = slot;
                         vc->q_tail = qt + 1;
-                        if (qh != qt && !over) {          // exchange
-                            next_slot = sm_uniform(vc->ring[qh & 15u]);
+                        vc->where[slot] = 4u;
+                        vc->origin[slot] = sp;
+                        if (give == 1) {
+                            const uint32_t head = sm_uniform(vc->ring[qh & 15u]);
                             vc->q_head = qh + 1;
-                        } else {                          // leave it
-                            keep = 0;
+                            vc->where[head] = sp;
+                            slot = head;
+                            action = 1;
+                        } else {
                             vc->sp_active[sp] = sm_uniform(vc->sp_active[sp]) - 1;
                             sm_rebalance(vc, s.n_slots);
                             last_slot = slot;
-                            patience = over ? 0u : 100u;
+                            patience = give == 2 ? 0u : 300u;
+                            action = 2;
                         }
                     }
                     sm_unlock(ctl);
-                    if (!keep) { have = 0; break; }
-                    if (next_slot == slot) {   // nobody to exchange with: carry on (state is still in registers)
-                        // (re-entering run_lzma needs the same d / wc: loop with fresh = 0 would reload them from sv,
-                        // which was not written; so store them)
-                        sv->d = d; sv->wc = wc; sv->in = u_in; sv->out = u_out; sv->ui = ui;
-                    }
-                    slot = next_slot;
-                    fresh = 0;
-                    continue;
+                    if (action) break;
                 }
+                if (action == 1) { fresh = 0; continue; }
+                if (action == 2) { have = 0; break; }
                 lzma1_finish(d, u_in, u_out, a.results[ui]);
             }
             // ---- the unit is done: start the launch's next one in this slot, or retire
@@ -356,6 +407,8 @@ __global__ void __launch_bounds__(32 * kSmMaxSlots, 1) lzgpu_sm_kernel(const KAr
             vc->dry = 1;
             vc->live = sm_uniform(vc->live) - 1;
             vc->sp_active[sp] = sm_uniform(vc->sp_active[sp]) - 1;
+            vc->where[slot] = 4u;
+            vc->rem[slot] = 0xffffffffu;
             sm_rebalance(vc, s.n_slots);
             sm_unlock(ctl);
             have = 0;
@@ -644,7 +697,8 @@ struct lzgpu_plan {
     bool borrowed = false;                // d_units / d_order / d_results live in the device's descriptor arena
     int variant = 0;
     int max_ctas_per_sm = 0;              // 0: as many as fit (14 at lc3 lp0 pb2)
-    uint32_t rotate_every = 16;           // SM-resident scheduler: refills between two exchange offers of a warp (LZGPU_ROTATE)
+    uint32_t rotate_every = 16;           // SM-resident scheduler: refills between two looks for an exchange (LZGPU_ROTATE)
+    uint32_t rotate_mode = 0;             // 0: exchange towards "more work left on the less crowded sub-partition"; 1: blind (LZGPU_ROTATE_MODE)
 };
 
 extern "C" int lzgpu_ctx_create(const int *devices, int n_devices, lzgpu_ctx **out) {
@@ -734,6 +788,7 @@ static int plan_create_impl(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *uni
     p->variant = decoder_variant();
     if (const char *e = getenv("LZGPU_MAX_CTAS_PER_SM")) p->max_ctas_per_sm = atoi(e);
     if (const char *e = getenv("LZGPU_ROTATE")) p->rotate_every = (uint32_t)atoi(e);
+    if (const char *e = getenv("LZGPU_ROTATE_MODE")) p->rotate_mode = (uint32_t)atoi(e);
     p->n = n;
     p->in_size = in_size;
     p->out_size = out_size;
@@ -925,6 +980,7 @@ extern "C" int lzgpu_plan_launch(lzgpu_plan *p, const uint8_t *d_in, uint8_t *d_
             sa.slot_bytes = L.sm_slot_bytes;
             sa.save_off = L.sm_slot_bytes - kSmSaveBytes;
             sa.rotate_every = p->rotate_every;
+            sa.rotate_mode = p->rotate_mode;
             sa.next = p->d_next + li;
             CUDA_TRY(cudaMemsetAsync(sa.next, 0, sizeof(uint32_t), ls));
             const size_t sm_bytes = kSmCtlBytes + (size_t)L.sm_slots * L.sm_slot_bytes;

@@ -282,7 +282,7 @@ LZ_DEV void f2_leave(Dec &d) {
 // the same Dec / WarpCopy contents) it carries on with that refill.
 enum : int { RUN_DONE = 0, RUN_YIELD = 1 };
 struct NoYield {
-    LZ_DEV bool want() { return false; }
+    LZ_DEV bool want(const Dec &) { return false; }
 };
 
 template <int kV, class Yield = NoYield>
@@ -301,7 +301,7 @@ LZ_DEV int run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8_
                         if (op != OP_SWITCH) break;
                         // stage used up (refill) or the unit's tail reached (careful decoder from here on)
                         publish_progress(d, wc);
-                        if (yield.want()) {
+                        if (yield.want(d)) {
                             LZ_CP_WAIT();   // window-copy sources this warp's cp.async is still fetching into the copy stage
                             LZ_SYNC();
                             return RUN_YIELD;
