@@ -83,8 +83,7 @@ __global__ void __launch_bounds__(32, LZGPU_MIN_CTAS) lzgpu_decode_kernel(const 
 //     idle warp of a sub-partition with fewer (targets: the live units spread evenly over the four);
 //   * a warp whose unit is done takes the next unit of the launch from a global counter (longest compressed first,
 //     as before); the first wave is assigned statically (unit w * grid + cta), one unit of every size band per CTA.
-// LZMA1 units are time-sliced; an LZMA2 group runs to completion on the warp that started it (its chunk walk keeps
-// state outside Dec), but takes part in everything else.
+// Both kinds of unit are time-sliced: an LZMA2 group's chunk walk keeps its state in Lz2Walk, saved with the rest.
 struct SmArgs {
     uint32_t count;          // units of this launch (slots [slot0, slot0 + count) of `order`)
     uint32_t n_slots;        // units resident per CTA = warps per CTA
@@ -110,9 +109,11 @@ struct SmCtl {
 struct SmSaved {
     Dec d;
     WarpCopy wc;
+    Lz2Walk w;               // LZMA2 groups only
     const uint8_t *in;
     uint8_t *out;
     int32_t ui;
+    uint32_t lzma2;
 };
 constexpr uint32_t kSmCtlBytes = 320;   // >= sizeof(SmCtl), multiple of 16
 constexpr uint32_t kSmSaveBytes = (sizeof(SmSaved) + 15u) & ~15u;
@@ -202,9 +203,10 @@ __device__ __forceinline__ uint32_t sm_accept(volatile SmCtl *c, uint32_t sp, ui
 struct SmYield {
     volatile SmCtl *c;
     uint32_t sp, every, mode, n_slots, slot, refills, intent, rem;
+    const uint8_t *unit_end;   // end of the unit's compressed bytes (an LZMA2 group: of its last chunk)
     __device__ __forceinline__ bool want(const Dec &d) {
         refills++;
-        rem = (uint32_t)(d.in_end - (d.g0 + (d.ips - d.sIn)));
+        rem = (uint32_t)(unit_end - (d.g0 + (d.ips - d.sIn)));
         c->rem[slot] = rem;
         uint32_t it = 0;
         if (sm_accept(c, sp, rem, mode)) it = 1;
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(32 * kSmMaxSlots, 1) lzgpu_sm_kernel(const KAr
     }
     __syncthreads();
 
-    SmYield yield{vc, sp, s.rotate_every, s.rotate_mode, s.n_slots, 0, 0, 0, 0};
+    SmYield yield{vc, sp, s.rotate_every, s.rotate_mode, s.n_slots, 0, 0, 0, 0, nullptr};
 #ifdef LZGPU_SM_WATCHDOG
     uint32_t idle_polls = 0;
 #endif
@@ -313,9 +315,11 @@ __global__ void __launch_bounds__(32 * kSmMaxSlots, 1) lzgpu_sm_kernel(const KAr
             io.inbuf = io.stage + 128;
             Dec d;
             WarpCopy wc;
+            Lz2Walk w;
             const uint8_t *u_in;
             uint8_t *u_out;
             int32_t ui;
+            uint32_t lzma2;
             bool resume, run = true;
             if (fresh) {
                 ui = a.order[a.slot0 + idx];
@@ -328,13 +332,12 @@ __global__ void __launch_bounds__(32 * kSmMaxSlots, 1) lzgpu_sm_kernel(const KAr
                 u_in = io.in;
                 u_out = io.out;
                 resume = false;
+                lzma2 = u.kind == LZGPU_KIND_LZMA2_GROUP ? 1u : 0u;
                 vc->where[slot] = sp;
-                if (u.kind == LZGPU_KIND_LZMA2_GROUP) {
-                    vc->rem[slot] = 0xffffffffu;
-                    run_unit_lzma2<kV>(u, io, P, L, a.lit_bits_cap, a.results[ui]);
-                    run = false;
+                vc->rem[slot] = u.in_len > 0xfffffffeull ? 0xfffffffeu : (uint32_t)u.in_len;
+                if (lzma2) {
+                    lzma2_start<kV>(u, io, P, a.lit_bits_cap, d, wc, w);
                 } else {
-                    vc->rem[slot] = u.in_len > 0xfffffffeull ? 0xfffffffeu : (uint32_t)u.in_len;
                     run = lzma1_start<kV>(u, io, P, L, d, wc);
                     if (!run) lzma1_finish(d, u_in, u_out, a.results[ui]);
                 }
@@ -344,6 +347,8 @@ __global__ void __launch_bounds__(32 * kSmMaxSlots, 1) lzgpu_sm_kernel(const KAr
                 u_in = sv->in;
                 u_out = sv->out;
                 ui = sv->ui;
+                lzma2 = sv->lzma2;
+                if (lzma2) w = sv->w;
                 resume = true;
             }
             if (run) {
@@ -352,7 +357,13 @@ __global__ void __launch_bounds__(32 * kSmMaxSlots, 1) lzgpu_sm_kernel(const KAr
                 uint32_t action = 0;   // 1: carry on with the unit in `slot` (another one after an exchange), 2: idle
                 for (;;) {
                     yield.slot = slot;
-                    r = run_lzma<kV, SmYield>(d, wc, P, L, u_out, io.inbuf, yield, resume);
+                    if (lzma2) {
+                        yield.unit_end = w.in_end;
+                        r = lzma2_walk<kV, SmYield>(d, wc, w, P, L, io.inbuf, yield, resume);
+                    } else {
+                        yield.unit_end = d.in_end;
+                        r = run_lzma<kV, SmYield>(d, wc, P, L, u_out, io.inbuf, yield, resume);
+                    }
                     if (r != RUN_YIELD) break;
                     resume = true;
                     sm_lock(ctl);
@@ -364,9 +375,11 @@ __global__ void __launch_bounds__(32 * kSmMaxSlots, 1) lzgpu_sm_kernel(const KAr
                     if (give) {
                         sv->d = d;
                         sv->wc = wc;
+                        if (lzma2) sv->w = w;
                         sv->in = u_in;
                         sv->out = u_out;
                         sv->ui = ui;
+                        sv->lzma2 = lzma2;
                         vc->ring[qt & 15u] = slot;
                         vc->q_tail = qt + 1;
                         vc->where[slot] = 4u;
@@ -390,7 +403,8 @@ __global__ void __launch_bounds__(32 * kSmMaxSlots, 1) lzgpu_sm_kernel(const KAr
                 }
                 if (action == 1) { fresh = 0; continue; }
                 if (action == 2) { have = 0; break; }
-                lzma1_finish(d, u_in, u_out, a.results[ui]);
+                if (lzma2) lzma2_finish(d, w, a.results[ui]);
+                else lzma1_finish(d, u_in, u_out, a.results[ui]);
             }
             // ---- the unit is done: start the launch's next one in this slot, or retire
             uint32_t nidx = 0xffffffffu;

@@ -355,6 +355,10 @@ __device__ __forceinline__ uint32_t f2_lds16(uint32_t a) {
 // than 2^31 > code, so the minimum keeps code (R >> j < 2^31).  The serial chain per bit is SUB -> MIN (10 cycles); the
 // predicated form (setp -> @p sub) pays the 13-cycle guard latency in every step (18 cycles, profiles/r02_ubench.txt).
 // The bits are read off afterwards (a step that changed code decided 1), outside the chain.
+// prefetch of the match source before the align bits are decoded
+#ifndef F2_PF_SRC
+#define F2_PF_SRC 1
+#endif
 #ifndef F2_DMIN
 #define F2_DMIN 1
 #endif
@@ -588,6 +592,15 @@ __device__ __forceinline__ uint32_t decode_fast2(Dec &d, WarpCopy &wc, uint32_t 
                         d.range >>= n;
                     }
                     dist += res << 4;
+#if F2_PF_SRC
+                    // the match source is now known to within the 4 align bits: ask for its line(s) before they are
+                    // decoded -- a literal that follows the match waits for the source bytes (prevByte, matchByte),
+                    // and the align tree is 150 cycles of head start on a 260 (L2) ... 800 (DRAM) cycle fetch
+                    {
+                        const uint8_t *pf = d.outp - dist - 16u;
+                        asm volatile("prefetch.global.L1 [%0];\n\tprefetch.global.L1 [%0+48];" : : "l"(pf));
+                    }
+#endif
                     uint32_t m;
                     F2_TREE4(d, m, sP + 2u * Y::ALIGN, al0, al2, al3);   // :580-625
                     dist += __brev(m) >> 28;

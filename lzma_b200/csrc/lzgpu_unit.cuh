@@ -517,11 +517,18 @@ LZ_DEV void run_unit_lzma1(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
 }
 
 // LZMA2 group: walk the chunks (Reader2.startChunk + Read, reader2.go:100-250).
+// Everything the walk keeps between two chunks -- and inside an LZMA chunk, while run_lzma decodes it -- lives in
+// Lz2Walk, so that the walk can be left where run_lzma yields and taken up again by another warp (time slicing).
+struct Lz2Walk {
+    const uint8_t *in, *ip, *in_end, *payload, *dict_base;
+    uint8_t *out, *out_limit;
+    uint64_t in_len, in_rem, consumed;
+    uint32_t have_coder, props, csz, short_payload, flags, lit_bits_cap;
+    int32_t status, site;
+};
+
 template <int kV>
-LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, uint16_t *L,
-                           uint32_t lit_bits_cap, lzgpu_result &res) {
-    Dec d;
-    WarpCopy wc;
+LZ_DEV void lzma2_start(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, uint32_t lit_bits_cap, Dec &d, WarpCopy &wc, Lz2Walk &w) {
     wc.pend_len = 0;
     wc.pend_dst = io.out;
     wc.pend_staged = 0;
@@ -549,28 +556,48 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
     d.inb_hi = d.inb_lo = 0;
     d.inbits = 0;
     d.phantom = 0;
+    d.nextw = 0;
     d.outp = io.out;
     d.out_end = io.out;
+    d.ip = io.in;
+    d.in_end = io.in;
     d.end_is_size = 1;
     d.size_defined = 1;
     d.status = LZGPU_OK;
     d.site = 0;
 
-    const uint8_t *ip = io.in;                 // chunk cursor (uniform)
-    const uint8_t *const in_end = io.in + io.in_len;
-    uint8_t *const out_limit = io.out + io.out_cap;
-    const uint8_t *dict_base = io.out;         // window.Reset() moves it (window.go:135-140)
-    uint32_t have_coder = 0;                   // r.lzmaReader != nil, for this unit
-    uint32_t props = ((uint32_t)u.pb * 5 + u.lp) * 9 + u.lc;  // r.header[5]: persists between chunks (Q8)
-    int32_t status = LZGPU_OK, site = 0;
-    uint64_t consumed = 0;
+    w.in = io.in;
+    w.in_len = io.in_len;
+    w.ip = io.in;                              // chunk cursor (uniform)
+    w.in_end = io.in + io.in_len;
+    w.payload = io.in;
+    w.out = io.out;
+    w.out_limit = io.out + io.out_cap;
+    w.dict_base = io.out;                      // window.Reset() moves it (window.go:135-140)
+    w.have_coder = 0;                          // r.lzmaReader != nil, for this unit
+    w.props = ((uint32_t)u.pb * 5 + u.lp) * 9 + u.lc;  // r.header[5]: persists between chunks (Q8)
+    w.csz = 0;
+    w.short_payload = 0;
+    w.in_rem = 0;
+    w.flags = u.flags;
+    w.lit_bits_cap = lit_bits_cap;
+    w.status = LZGPU_OK;
+    w.site = 0;
+    w.consumed = 0;
+}
 
+// Walks until the group ends (RUN_DONE: w.status / w.site / w.consumed hold the verdict) or run_lzma yields inside an
+// LZMA chunk (RUN_YIELD; call again with resume = true and the same d / wc / w).
+template <int kV, class Yield>
+LZ_DEV int lzma2_walk(Dec &d, WarpCopy &wc, Lz2Walk &w, uint16_t *P, uint16_t *L, uint8_t *inbuf, Yield &yield, bool resume) {
     for (;;) {
+        if (!resume) {
         // ---- startChunk: lane 0 reads the header, everybody gets the verdict ----
+        const uint8_t *ip = w.ip;
         uint32_t ctrl = 0, hdr = 0;  // hdr: [0]=end [1]=eof ; usz, csz below
         uint32_t usz = 0, csz = 0, newprops = 0xFFFFFFFFu;
         {
-            const uint64_t rem = (uint64_t)(in_end - ip);
+            const uint64_t rem = (uint64_t)(w.in_end - ip);
             if (rem == 0) {
                 hdr = 2;  // ran off the unit: fine between units, UnexpectedEOF at the stream's end
             } else {
@@ -594,28 +621,28 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
             }
         }
         if (hdr != 0) {
-            if (hdr == 1) { consumed = (uint64_t)(ip - io.in) + 1; status = LZGPU_OK; }
+            if (hdr == 1) { w.consumed = (uint64_t)(ip - w.in) + 1; w.status = LZGPU_OK; }
             else {
-                consumed = hdr == 3 ? io.in_len : (uint64_t)(ip - io.in);
-                status = (hdr == 3 || (u.flags & LZGPU_UF_LZMA2_LAST)) ? LZGPU_UNEXPECTED_EOF : LZGPU_OK;
+                w.consumed = hdr == 3 ? w.in_len : (uint64_t)(ip - w.in);
+                w.status = (hdr == 3 || (w.flags & LZGPU_UF_LZMA2_LAST)) ? LZGPU_UNEXPECTED_EOF : LZGPU_OK;
             }
             break;
         }
         const uint32_t hl = ctrl < 0x80 ? 3 : (ctrl < 0xC0 ? 5 : 6);
         const uint8_t *payload = ip + hl;
-        if (newprops != 0xFFFFFFFFu) props = newprops;
+        if (newprops != 0xFFFFFFFFu) w.props = newprops;
 
         if (ctrl == 1 || ctrl >= 0xE0) {  // dictionary reset (:132-134)
-            dict_base = d.outp;
+            w.dict_base = d.outp;
             d.wpos = 0;
             d.full = 0;
         }
 
         if (ctrl < 0x80) {  // ---- uncompressed chunk: uncompressedRead (:252-294) ----
-            uint64_t n = (uint64_t)(in_end - payload);
+            uint64_t n = (uint64_t)(w.in_end - payload);
             const bool short_payload = n < usz;
             if (!short_payload) n = usz;
-            if ((uint64_t)(out_limit - d.outp) < n) { status = LZGPU_OUTPUT_OVERFLOW; consumed = (uint64_t)(payload - io.in); break; }
+            if ((uint64_t)(w.out_limit - d.outp) < n) { w.status = LZGPU_OUTPUT_OVERFLOW; w.consumed = (uint64_t)(payload - w.in); break; }
             uint8_t *dst = d.outp;
             warp_copy_in(dst, payload, (uint32_t)n);     // n <= 65 536
             LZ_SYNC();
@@ -623,41 +650,41 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
             uint64_t wp = (uint64_t)d.wpos + n;      // window.ReadFrom, window.go:142-155
             while (wp >= d.dict_size) { wp -= d.dict_size; d.full = 1; }
             d.wpos = (uint32_t)wp;
-            ip = payload + n;
+            w.ip = payload + n;
             if (short_payload) {  // the next header read hits EOF (:103-110)
-                status = LZGPU_UNEXPECTED_EOF; consumed = io.in_len; break;
+                w.status = LZGPU_UNEXPECTED_EOF; w.consumed = w.in_len; break;
             }
             continue;
         }
 
         // ---- LZMA chunk ----
-        if (!have_coder) {
+        if (!w.have_coder) {
             // First LZMA chunk of the unit.  At the start of a stream the reference builds
             // a new coder from header[5] whatever the control byte (reader2.go:146-153).
             // Elsewhere the scanner only cuts units where the chunk resets the state.
-            if (!(u.flags & LZGPU_UF_LZMA2_FRESH) && ctrl < 0xA0) {
-                status = LZGPU_RESULT_ERROR; site = LZGPU_SITE_LZMA2_NO_STATE; consumed = (uint64_t)(ip - io.in); break;
+            if (!(w.flags & LZGPU_UF_LZMA2_FRESH) && ctrl < 0xA0) {
+                w.status = LZGPU_RESULT_ERROR; w.site = LZGPU_SITE_LZMA2_NO_STATE; w.consumed = (uint64_t)(ip - w.in); break;
             }
         }
-        if (!have_coder || ctrl >= 0xA0) {
-            if (!have_coder || ctrl >= 0xC0) {      // DecodeProp(header[5]) + Renew (:158-165)
-                if (props >= 225) { status = LZGPU_INCORRECT_PROPERTIES; consumed = (uint64_t)(ip - io.in); break; }
-                const uint32_t lc = props % 9, r = props / 9, pb = r / 5, lp = r % 5;
-                if (lc + lp > lit_bits_cap || pb > LZ_LAY(kV)::PB) {   // tables of this launch too small: the unit lied
-                    status = LZGPU_RESULT_ERROR; site = LZGPU_SITE_LZMA2_PROPS; consumed = (uint64_t)(ip - io.in); break;
+        if (!w.have_coder || ctrl >= 0xA0) {
+            if (!w.have_coder || ctrl >= 0xC0) {      // DecodeProp(header[5]) + Renew (:158-165)
+                if (w.props >= 225) { w.status = LZGPU_INCORRECT_PROPERTIES; w.consumed = (uint64_t)(ip - w.in); break; }
+                const uint32_t lc = w.props % 9, r = w.props / 9, pb = r / 5, lp = r % 5;
+                if (lc + lp > w.lit_bits_cap || pb > LZ_LAY(kV)::PB) {   // tables of this launch too small: the unit lied
+                    w.status = LZGPU_RESULT_ERROR; w.site = LZGPU_SITE_LZMA2_PROPS; w.consumed = (uint64_t)(ip - w.in); break;
                 }
                 set_props(d, lc, lp, pb);
             }
             uint32_t lb = d.lc, m = d.lp_mask;
             while (m) { lb++; m >>= 1; }
             coder_reset<kV>(d, P, L, lb);                // s.Reset() (:156-157) / newState
-            have_coder = 1;
+            w.have_coder = 1;
         }
-        const uint64_t in_rem = (uint64_t)(in_end - payload);
+        const uint64_t in_rem = (uint64_t)(w.in_end - payload);
         const bool short_payload = in_rem < csz;
         d.ip = payload;
         d.in_end = payload + (short_payload ? in_rem : (uint64_t)csz);   // limitByteReader(in, cs)
-        const uint64_t cap_left = (uint64_t)(out_limit - d.outp);
+        const uint64_t cap_left = (uint64_t)(w.out_limit - d.outp);
         d.size_defined = 1;                          // Reopen -> SetUnpackSize(us) (reader1.go:166-176)
         d.end_is_size = usz <= cap_left;
         d.out_end = d.outp + (d.end_is_size ? (uint64_t)usz : cap_left);
@@ -666,60 +693,76 @@ LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, u
         int32_t r = 0;
         r = rc_init(d);
         if (r != 0) {
-            consumed = (uint64_t)(payload - io.in);
-            if (r < 0) { status = LZGPU_UNEXPECTED_EOF; consumed = io.in_len; }
-            else { status = LZGPU_RESULT_ERROR; site = LZGPU_SITE_RC_INIT; }
+            w.consumed = (uint64_t)(payload - w.in);
+            if (r < 0) { w.status = LZGPU_UNEXPECTED_EOF; w.consumed = w.in_len; }
+            else { w.status = LZGPU_RESULT_ERROR; w.site = LZGPU_SITE_RC_INIT; }
             break;
         }
-        reload_context<kV>(d, dict_base);
-        run_lzma<kV>(d, wc, P, L, dict_base, io.inbuf);
+        reload_context<kV>(d, w.dict_base);
+        w.payload = payload;
+        w.csz = csz;
+        w.short_payload = short_payload ? 1u : 0u;
+        w.in_rem = in_rem;
+        }
+        if (run_lzma<kV, Yield>(d, wc, P, L, w.dict_base, inbuf, yield, resume) == RUN_YIELD) return RUN_YIELD;
+        resume = false;
 
         // what the chunk did, as seen by every lane
-        uint32_t st = (uint32_t)d.status, st_site = (uint32_t)d.site, complete = 0, exact = 0;
-        uint64_t outbits = 0;
-        complete = d.outp == d.out_end && d.end_is_size;
-        exact = rc_consumed(d, payload) == (uint64_t)(d.in_end - payload);
-        outbits = (uint64_t)(uintptr_t)d.outp;
-        d.outp = (uint8_t *)(uintptr_t)outbits;
-        // keep the uniform window position in step with lane 0's
-        uint32_t wpos = d.wpos, full = d.full;
-        d.wpos = wpos;
-        d.full = full;
+        const uint8_t *payload = w.payload;
+        const uint32_t csz = w.csz;
+        const bool short_payload = w.short_payload != 0;
+        const uint64_t in_rem = w.in_rem;
+        const uint32_t st = (uint32_t)d.status, st_site = (uint32_t)d.site;
+        const bool complete = d.outp == d.out_end && d.end_is_size;
+        const bool exact = rc_consumed(d, payload) == (uint64_t)(d.in_end - payload);
 
-        consumed = (uint64_t)(payload - io.in) + (short_payload ? in_rem : (uint64_t)csz);
+        w.consumed = (uint64_t)(payload - w.in) + (short_payload ? in_rem : (uint64_t)csz);
         if (st == LZGPU_OK || st == LZGPU_OK_INPUT_EXHAUSTED) {
             if (!complete) {
                 // The coder wanted more input than the chunk holds.  At the end of a truncated
                 // stream the reference reports io.ErrUnexpectedEOF at the next header read;
                 // otherwise it would carry on with a short chunk (Q1/Q8): documented deviation.
-                if (short_payload) { status = LZGPU_UNEXPECTED_EOF; consumed = io.in_len; }
-                else { status = LZGPU_RESULT_ERROR; site = LZGPU_SITE_LZMA2_CHUNK_SIZE; }
+                if (short_payload) { w.status = LZGPU_UNEXPECTED_EOF; w.consumed = w.in_len; }
+                else { w.status = LZGPU_RESULT_ERROR; w.site = LZGPU_SITE_LZMA2_CHUNK_SIZE; }
                 break;
             }
             if (st == LZGPU_OK && !exact) {
                 // Decoded size reached with compressed bytes left over: the reference parses the
                 // next header from the middle of the payload (Q8).  Documented deviation.
-                status = LZGPU_RESULT_ERROR; site = LZGPU_SITE_LZMA2_CHUNK_SIZE;
+                w.status = LZGPU_RESULT_ERROR; w.site = LZGPU_SITE_LZMA2_CHUNK_SIZE;
                 break;
             }
-            if (short_payload) { status = LZGPU_UNEXPECTED_EOF; consumed = io.in_len; break; }
-            ip = payload + csz;
+            if (short_payload) { w.status = LZGPU_UNEXPECTED_EOF; w.consumed = w.in_len; break; }
+            w.ip = payload + csz;
             continue;
         }
-        status = (int32_t)st;
-        site = (int32_t)st_site;
+        w.status = (int32_t)st;
+        w.site = (int32_t)st_site;
         break;
     }
+    return RUN_DONE;
+}
 
-    uint32_t code = d.code;
-    uint64_t outbits = (uint64_t)(uintptr_t)d.outp;
+LZ_DEV void lzma2_finish(const Dec &d, const Lz2Walk &w, lzgpu_result &res) {
     LZ_IF_LANE0_ONLY {
-        res.status = status;
-        res.err_site = site;
-        res.bytes_out = (uint64_t)((uint8_t *)(uintptr_t)outbits - io.out);
-        res.bytes_in = consumed;
-        res.final_code = code;
+        res.status = w.status;
+        res.err_site = w.site;
+        res.bytes_out = (uint64_t)(d.outp - w.out);
+        res.bytes_in = w.consumed;
+        res.final_code = d.code;
     }
+}
+
+template <int kV>
+LZ_DEV void run_unit_lzma2(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, uint16_t *L,
+                           uint32_t lit_bits_cap, lzgpu_result &res) {
+    Dec d;
+    WarpCopy wc;
+    Lz2Walk w;
+    NoYield ny;
+    lzma2_start<kV>(u, io, P, lit_bits_cap, d, wc, w);
+    lzma2_walk<kV, NoYield>(d, wc, w, P, L, io.inbuf, ny, false);
+    lzma2_finish(d, w, res);
 }
 
 }  // namespace lzgpu

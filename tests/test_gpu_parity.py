@@ -609,3 +609,29 @@ def test_sm_scheduler_with_bad_units_and_lzma2(monkeypatch):
             assert got == l2_plain
             k += 4
     assert n_bad > 100
+
+
+@pytest.mark.parametrize("rotate", ["1", "16"])
+def test_sm_scheduler_slices_lzma2_groups(rotate, monkeypatch):
+    """LZMA2 groups are time-sliced too (the chunk walk's state travels with the unit): one raw LZMA2 stream of 2 400
+    groups of very different sizes -- text, incompressible data (uncompressed chunks) and mixed -- 16 per SM, exchanged
+    between warps inside their LZMA chunks.  Compared with the plaintext, group by group."""
+    monkeypatch.setenv("LZGPU_ROTATE", rotate)
+    blocks = []
+    for i in range(30):
+        size = (20 + 41 * (i % 7)) << 10
+        blocks.append((K.text_block, K.random_block, K.mixed_block)[i % 3](9100 + i, size))
+    parts = [K.compress_raw_lzma2(b, dict_size=1 << 20) for b in blocks]
+    n_groups = 2400
+    seq = [(k * 11 + k // 30) % 30 for k in range(n_groups)]
+    stream = b"".join(parts[i][:-1] for i in seq[:-1]) + parts[seq[-1]]
+    with B.Context([0]) as c:
+        units, total, sst = B.scan_lzma2(stream, 1 << 20)
+        assert sst == L.OK and len(units) == n_groups and total == sum(len(blocks[i]) for i in seq)
+        st, site, data = B.decode_lzma2_stream(c, stream, 1 << 20)
+    assert st == L.OK and len(data) == total
+    off = 0
+    for k, i in enumerate(seq):
+        n = len(blocks[i])
+        assert data[off:off + n] == blocks[i], f"group {k} (block {i})"
+        off += n
