@@ -187,6 +187,10 @@ if __name__ == "__main__":
                 f = spec.split(":")
                 run(ctx, f[0], int(f[1]), (int(f[2]) if len(f) > 2 else 1) << 20)
             sys.exit(0)
+        if "--lzma2" in sys.argv:          # BASELINE config 3's shape, and twice as many units (14 per SM)
+            run_lzma2(ctx, 1024, 1 << 20)
+            run_lzma2(ctx, 2072, 1 << 20)
+            sys.exit(0)
         if "--quick-random" in sys.argv:   # incompressible data: 9 adaptive bits per byte, literals only
             run(ctx, "random", 148, 1 << 20)
             run(ctx, "mixed", 1024, 1 << 20)
