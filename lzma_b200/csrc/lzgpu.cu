@@ -40,6 +40,8 @@ struct KArgs {
     uint32_t slot0;              // first slot of this launch in `order`
     uint32_t stage_off;          // uint16 index of the 64-byte staging buffer inside the shared array
     uint32_t *progress;          // per unit: decoded bytes that are final in HBM, in 64 KiB blocks (host-mapped; may be null)
+    uint8_t *hout_base;          // push mode: device view of the caller's pinned output buffer (else null) ...
+    const uint64_t *hout_off;    // ... and where in it each unit's output goes (host-mapped, indexed like `units`)
 };
 
 // One warp per CTA, one unit per warp.  Fixed tables (3.7 KB) always in shared
@@ -63,6 +65,7 @@ __global__ void __launch_bounds__(32, LZGPU_MIN_CTAS) lzgpu_decode_kernel(const 
     io.stage = reinterpret_cast<uint8_t *>(smem_probs + a.stage_off);
     io.inbuf = io.stage + 128;
     io.progress = a.progress ? a.progress + ui : nullptr;
+    io.hout = a.hout_base ? a.hout_base + a.hout_off[ui] : nullptr;
     lzgpu_result &res = a.results[ui];
     if (u.kind == LZGPU_KIND_LZMA2_GROUP) run_unit_lzma2<kV>(u, io, P, L, a.lit_bits_cap, res);
     else run_unit_lzma1<kV>(u, io, P, L, res);
@@ -204,6 +207,9 @@ struct SmYield {
     volatile SmCtl *c;
     uint32_t sp, every, mode, n_slots, slot, refills, intent, rem;
     const uint8_t *unit_end;   // end of the unit's compressed bytes (an LZMA2 group: of its last chunk)
+    // push mode: the decoding warp writes its finished blocks to the caller's buffer itself.  (A spare warp per CTA doing
+    // it for the others was tried: 113.3 -> 114.2 ms end to end -- its copies and the queue cost more than the waits.)
+    __device__ __forceinline__ void push(const Dec &d, uint64_t from, uint64_t to) { push_out(d, from, to); }
     __device__ __forceinline__ bool want(const Dec &d) {
         refills++;
         rem = (uint32_t)(unit_end - (d.g0 + (d.ips - d.sIn)));
@@ -329,6 +335,7 @@ __global__ void __launch_bounds__(32 * kSmMaxSlots, 1) lzgpu_sm_kernel(const KAr
                 io.out = a.out_base + u.out_off;
                 io.out_cap = u.out_cap;
                 io.progress = a.progress ? a.progress + ui : nullptr;
+                io.hout = a.hout_base ? a.hout_base + a.hout_off[ui] : nullptr;
                 u_in = io.in;
                 u_out = io.out;
                 resume = false;
@@ -703,6 +710,8 @@ struct lzgpu_plan {
     lzgpu_result *d_results = nullptr;
     uint16_t *d_lit_ws = nullptr;
     uint32_t *d_progress = nullptr;       // optional, set by the host-buffer entry point
+    uint8_t *d_hout_base = nullptr;       // push mode (host-buffer entry point, pinned output): see KArgs
+    const uint64_t *d_hout_off = nullptr;
     uint32_t *d_next = nullptr;           // one unit counter per launch (SM-resident scheduler)
     uint64_t lit_ws_stride = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -979,6 +988,8 @@ extern "C" int lzgpu_plan_launch(lzgpu_plan *p, const uint8_t *d_in, uint8_t *d_
         a.slot0 = L.slot0;
         a.stage_off = (uint32_t)probs_elems(L.lit_bits, L.lit_global, L.pb2);
         a.progress = p->d_progress;
+        a.hout_base = p->d_hout_base;
+        a.hout_off = p->d_hout_off;
         size_t smem = L.smem;
         if (p->max_ctas_per_sm >= 5) {
             // occupancy cap (experiments, and the single-wave heuristic of plan_create): asking for more shared memory
@@ -998,8 +1009,9 @@ extern "C" int lzgpu_plan_launch(lzgpu_plan *p, const uint8_t *d_in, uint8_t *d_
             sa.next = p->d_next + li;
             CUDA_TRY(cudaMemsetAsync(sa.next, 0, sizeof(uint32_t), ls));
             const size_t sm_bytes = kSmCtlBytes + (size_t)L.sm_slots * L.sm_slot_bytes;
-            if (L.pb2) lzgpu_sm_kernel<33 | V_PB2><<<L.sm_grid, 32 * L.sm_slots, sm_bytes, ls>>>(a, sa);
-            else lzgpu_sm_kernel<33><<<L.sm_grid, 32 * L.sm_slots, sm_bytes, ls>>>(a, sa);
+            const unsigned threads = 32u * L.sm_slots;
+            if (L.pb2) lzgpu_sm_kernel<33 | V_PB2><<<L.sm_grid, threads, sm_bytes, ls>>>(a, sa);
+            else lzgpu_sm_kernel<33><<<L.sm_grid, threads, sm_bytes, ls>>>(a, sa);
         } else if (L.lit_global) launch_decode<true>(p->variant, false, L.count, smem, ls, a);
         else launch_decode<false>(p->variant, L.pb2, L.count, smem, ls, a);
         CUDA_TRY(cudaGetLastError());
@@ -1333,10 +1345,14 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
     // blocks to the caller's buffer on a second stream, so that only each unit's tail is left to copy
     // when the kernel ends.  (LZGPU_NO_STREAM_D2H=1 restores kernel-then-copy.)
     const uint64_t kBlock = 64 << 10;
-    bool stream_out = sh.out_bytes >= ((uint64_t)32 << 20) && !getenv("LZGPU_NO_STREAM_D2H");
-    if (stream_out) {
-        if (!ds.copy_stream && cudaStreamCreateWithFlags(&ds.copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); stream_out = false; }
-        if (stream_out && ds.progress_cap < n) {
+    // Push mode: when the caller's output buffer is pinned and mapped, every unit writes its decoded bytes there itself,
+    // over PCIe, 64 KiB block by block as they become final and its tail when it ends (push_out, lzgpu_unit.cuh): no
+    // D2H copy, no polling thread, nothing left to do when the kernel ends.  (LZGPU_NO_PUSH_D2H=1: the streamed copies.)
+    bool push = zc_out != nullptr && !getenv("LZGPU_NO_PUSH_D2H");
+    bool stream_out = !push && sh.out_bytes >= ((uint64_t)32 << 20) && !getenv("LZGPU_NO_STREAM_D2H");
+    if (stream_out || push) {
+        if (stream_out && !ds.copy_stream && cudaStreamCreateWithFlags(&ds.copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); stream_out = false; }
+        if ((stream_out || push) && ds.progress_cap < n) {
             if (ds.h_progress) cudaFreeHost(ds.h_progress);
             if (ds.h_tails) cudaFreeHost(ds.h_tails);
             ds.h_progress = nullptr; ds.d_progress = nullptr; ds.h_tails = nullptr; ds.d_tails = nullptr; ds.progress_cap = 0;
@@ -1350,6 +1366,7 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
                 if (ds.h_tails) cudaFreeHost(ds.h_tails);
                 ds.h_progress = nullptr; ds.d_progress = nullptr; ds.h_tails = nullptr; ds.d_tails = nullptr;
                 stream_out = false;
+                push = false;
             } else {
                 ds.progress_cap = want;
             }
@@ -1357,6 +1374,11 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
         if (stream_out) {
             memset(ds.h_progress, 0, n * sizeof(uint32_t));
             plan->d_progress = ds.d_progress;
+        }
+        if (push) {
+            for (size_t k = 0; k < n; k++) ds.h_tails[k] = host_out_off[k];
+            plan->d_hout_base = zc_out;
+            plan->d_hout_off = ds.d_tails;
         }
     }
     cudaEvent_t e0, e1, e2, e3;
@@ -1434,7 +1456,7 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
         mark("kernel finished, tails enqueued");
         cudaEventRecord(e3, ds.copy_stream);
     } else {
-        if (sh.rc == 0) {
+        if (sh.rc == 0 && !push) {
             // one copy per run of units that are adjacent in the caller's buffer and filled to their capacity
             std::vector<size_t> ord(n);
             std::iota(ord.begin(), ord.end(), 0);

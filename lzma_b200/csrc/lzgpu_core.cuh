@@ -51,6 +51,9 @@
 // window byte -> 32-bit register, issued now, first touched when a literal needs it (anything
 // the compiler inserts in between -- a mask, a move -- would stall on the load right here)
 #define LZ_LD_WIN8(dst, p) asm volatile("ld.global.u8 %0, [%1];" : "=r"(dst) : "l"(p) : "memory")
+#define LZ_LD_WIN32_IF(dst, p, cond)  /* window (global), written by this kernel: coherent load */ \
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.u32 %0, [%1];\n\t}" \
+                 : "+r"(dst) : "l"(p), "r"((uint32_t)(cond)) : "memory")
 #define LZ_LD_IN32_IF(dst, p, cond)                                                     \
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}" \
                  : "+r"(dst) : "l"(p), "r"((uint32_t)(cond)))
@@ -67,6 +70,7 @@
 #define LZ_FUNNEL_R(lo, hi, sh) ((uint32_t)(((((uint64_t)(hi)) << 32 | (uint64_t)(lo)) >> ((sh) & 31))))
 #define LZ_SHR_CLAMP(x, sh) ((sh) >= 32 ? 0u : ((uint32_t)(x) >> (sh)))
 #define LZ_LD_IN32_IF(dst, p, cond) do { if (cond) (dst) = *(const uint32_t *)(p); } while (0)
+#define LZ_LD_WIN32_IF(dst, p, cond) do { if (cond) (dst) = *(const uint32_t *)(p); } while (0)
 #define LZ_LD_WIN8(dst, p) ((dst) = *(const uint8_t *)(p))
 #define LZ_CP_ASYNC4(sdst, gsrc) memcpy((sdst), (gsrc), 4)   /* value captured at issue, like the copy */
 #define LZ_CP_COMMIT() ((void)0)
@@ -137,7 +141,8 @@ struct Dec {
     // streamed D2H (host-buffer entry point): decoded bytes that are final, published in 64 KiB blocks
     uint32_t *prog;                 // host-mapped counter of this unit, or null
     const uint8_t *out0;            // start of the unit's output
-    uint32_t pub;                   // blocks published so far
+    uint32_t pub;                   // blocks published (or pushed) so far
+    uint8_t *hout;                  // push mode: where this unit's output goes in the caller's pinned buffer (device view), or null
 };
 
 // Input is consumed through a 64-bit lookahead register so that the per-bit
@@ -206,7 +211,10 @@ LZ_HD void rc_fill(Dec &d) {
 //               units whose pb is <= 2; not a tuning knob
 enum : int { V_FAST = 1, V_PREFETCH = 4, V_STAGE = 16, V_CHAIN = 32, V_PB2 = 64 };
 #define LZ_LAY(kV) Lay<((kV) & V_PB2) ? 2 : 4>
-constexpr uint32_t kF2Stage = 512;        // bytes of compressed input staged per refill (V_CHAIN)
+#ifndef LZGPU_F2_STAGE
+#define LZGPU_F2_STAGE 512
+#endif
+constexpr uint32_t kF2Stage = LZGPU_F2_STAGE;   // bytes of compressed input staged per refill (V_CHAIN): a multiple of 512
 constexpr uint32_t kF2Margin = 41;        // a symbol consumes <= 21 bytes; the byte-ahead read adds 1
 constexpr uint32_t kF2MinInput = 128;     // do not (re)enter the V_CHAIN fast decoder with less input left
 constexpr uint32_t kFastInMargin = 64;    // >= 48 bit steps of one symbol + one word loaded ahead + slack

@@ -108,14 +108,16 @@ LZ_DEV void wc_commit(WarpCopy &wc) {
 // funnel-shifted into place (consecutive chunks of a stream sit 3 header bytes apart, so source and destination
 // are rarely congruent).  Four vectors per lane are in flight per trip.  No word is loaded that does not lie
 // entirely inside [src rounded down to 4, src + n).
-LZ_DEV void warp_copy_in(uint8_t *dst, const uint8_t *src, uint32_t n) {
+template <bool kWindow>   // kWindow: the source is window bytes this kernel wrote (coherent loads), not read-only input
+LZ_DEV void warp_copy(uint8_t *dst, const uint8_t *src, uint32_t n) {
 #if defined(__CUDA_ARCH__)
     const uint32_t lane = LZ_LANE();
     uint32_t head = (uint32_t)((16u - ((uint32_t)(uintptr_t)dst & 15u)) & 15u);
     if (head > n) head = n;
     {
         uint32_t v = 0;
-        LZ_LDIN8_IF(v, src + (lane < head ? lane : 0u), lane < head);
+        if (kWindow) LZ_LDG8_IF(v, src + (lane < head ? lane : 0u), lane < head);
+        else LZ_LDIN8_IF(v, src + (lane < head ? lane : 0u), lane < head);
         LZ_STG8_IF(dst + lane, v, lane < head);
     }
     dst += head; src += head; n -= head;
@@ -132,7 +134,8 @@ LZ_DEV void warp_copy_in(uint8_t *dst, const uint8_t *src, uint32_t n) {
 #pragma unroll
             for (int k = 0; k < 5; k++) {
                 w[u][k] = 0;
-                LZ_LD_IN32_IF(w[u][k], q + 4 * k, live && (k < 4 || a != 0u));
+                if (kWindow) LZ_LD_WIN32_IF(w[u][k], q + 4 * k, live && (k < 4 || a != 0u));
+                else LZ_LD_IN32_IF(w[u][k], q + 4 * k, live && (k < 4 || a != 0u));
             }
         }
 #pragma unroll
@@ -145,11 +148,26 @@ LZ_DEV void warp_copy_in(uint8_t *dst, const uint8_t *src, uint32_t n) {
     const uint32_t done = 16u * nv, rest = n - done;                    // < 20 (a != 0) or < 16
     {
         uint32_t v = 0;
-        LZ_LDIN8_IF(v, src + done + (lane < rest ? lane : 0u), lane < rest);
+        if (kWindow) LZ_LDG8_IF(v, src + done + (lane < rest ? lane : 0u), lane < rest);
+        else LZ_LDIN8_IF(v, src + done + (lane < rest ? lane : 0u), lane < rest);
         LZ_STG8_IF(dst + done + lane, v, lane < rest);
     }
 #else
     memcpy(dst, src, n);
+#endif
+}
+LZ_DEV void warp_copy_in(uint8_t *dst, const uint8_t *src, uint32_t n) { warp_copy<false>(dst, src, n); }
+// Push mode (the caller's output buffer is pinned and mapped): the unit itself writes its decoded bytes to host memory,
+// over PCIe, as they become final -- [from, to) of its output range; no D2H copy follows the kernel.
+LZ_DEV void push_out(const Dec &d, uint64_t from, uint64_t to) {
+#if defined(__CUDA_ARCH__)
+    __threadfence_block();   // the bytes were stored by all lanes (and, after an exchange, by other warps of the CTA)
+    __syncwarp();
+    while (from < to) {
+        const uint64_t n = to - from < (1u << 20) ? to - from : (uint64_t)(1u << 20);
+        warp_copy<true>(d.hout + from, d.out0 + from, (uint32_t)n);
+        from += n;
+    }
 #endif
 }
 
@@ -216,13 +234,16 @@ LZ_DEV bool f2_enter(Dec &d, const uint8_t *gpos, uint8_t *inbuf) {
     {   // one 16-byte cp.async (LDGSTS) per lane, global -> shared with no register in between; predicated, not
         // branched (avail >= 112: lanes beyond it name chunk 0 and copy nothing).  It is awaited right away -- a
         // second stage to fill ahead would cost the 14th unit per SM, and a refill is 0.1 % of a unit's time.
-        const bool live = 16u * l + 16u <= avail;
-        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t"
-                     "@q cp.async.cg.shared.global [%0], [%1], 16;\n\t"
-                     "cp.async.commit_group;\n\t"
-                     "cp.async.wait_group 0;\n\t}"
-                     : : "r"(d.sIn + 16u * l), "l"(g0 + 16u * (live ? l : 0u)), "r"((uint32_t)live) : "memory");
-        const uint8_t *pf = g0 + kF2Stage + 128u * (l & 3u);
+#pragma unroll
+        for (uint32_t c = 0; c < kF2Stage / 512u; c++) {
+            const uint32_t i = l + 32u * c;
+            const bool live = 16u * i + 16u <= avail;
+            asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t"
+                         "@q cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+                         : : "r"(d.sIn + 16u * i), "l"(g0 + 16u * (live ? i : 0u)), "r"((uint32_t)live) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        const uint8_t *pf = g0 + kF2Stage + 128u * (l & (kF2Stage / 128u - 1u));
         if (pf >= d.in_end) pf = g0;                 // (same prefetch from every lane group: harmless)
         LZ_PREFETCH_L2(pf);
     }
@@ -244,9 +265,17 @@ LZ_DEV bool f2_enter(Dec &d, const uint8_t *gpos, uint8_t *inbuf) {
 }
 // Streamed D2H: tell the host how much of this unit's output is final (stored and never touched again),
 // in 64 KiB blocks.  Called from the stage-refill path only (every few hundred input bytes).
-LZ_DEV void publish_progress(Dec &d, const WarpCopy &wc) {
+template <class Yield>
+LZ_DEV void publish_progress(Dec &d, const WarpCopy &wc, Yield &yield) {
 #if defined(__CUDA_ARCH__)
-    if (d.prog) {
+    if (d.hout) {
+        const uint8_t *fin = wc.pend_len ? wc.pend_dst : d.outp;   // a pending window copy is not stored yet
+        const uint32_t blocks = (uint32_t)((uint64_t)(fin - d.out0) >> 16);
+        if (blocks != d.pub) {
+            yield.push(d, (uint64_t)d.pub << 16, (uint64_t)blocks << 16);   // this warp, or the CTA's pusher warp
+            d.pub = blocks;
+        }
+    } else if (d.prog) {
         const uint8_t *fin = wc.pend_len ? wc.pend_dst : d.outp;   // a pending window copy is not stored yet
         const uint32_t blocks = (uint32_t)((uint64_t)(fin - d.out0) >> 16);
         if (blocks != d.pub) {
@@ -283,6 +312,7 @@ LZ_DEV void f2_leave(Dec &d) {
 enum : int { RUN_DONE = 0, RUN_YIELD = 1 };
 struct NoYield {
     LZ_DEV bool want(const Dec &) { return false; }
+    LZ_DEV void push(const Dec &d, uint64_t from, uint64_t to) { push_out(d, from, to); }
 };
 
 template <int kV, class Yield = NoYield>
@@ -300,7 +330,7 @@ LZ_DEV int run_lzma(Dec &d, WarpCopy &wc, uint16_t *P, uint16_t *L, const uint8_
                         op = decode_fast2<kV>(d, wc, len, dist);
                         if (op != OP_SWITCH) break;
                         // stage used up (refill) or the unit's tail reached (careful decoder from here on)
-                        publish_progress(d, wc);
+                        publish_progress(d, wc, yield);
                         if (yield.want(d)) {
                             LZ_CP_WAIT();   // window-copy sources this warp's cp.async is still fetching into the copy stage
                             LZ_SYNC();
@@ -456,6 +486,7 @@ struct UnitIO {
     uint8_t *stage;          // 64 bytes of shared memory, 4-byte aligned (window-copy staging)
     uint8_t *inbuf;          // kF2Stage bytes of shared memory, 16-byte aligned (V_CHAIN input stage)
     uint32_t *progress;      // host-mapped progress counter of this unit (streamed D2H), or null
+    uint8_t *hout;           // push mode: the unit's output range in the caller's pinned buffer (device view), or null
 };
 
 // LZMA1 unit (kind RAW; ALONE units are converted by the host): set-up, symbol loop, verdict.  The three are separate so
@@ -473,6 +504,7 @@ LZ_DEV bool lzma1_start(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, uint
     set_shared_addrs<kV>(d, P, io.inbuf, io.stage);
     wc.s_stage = d.sStage;
     d.prog = io.progress;
+    d.hout = io.hout;
     d.out0 = io.out;
     d.pub = 0;
     d.dict_size = u.dict_size;
@@ -499,6 +531,7 @@ LZ_DEV bool lzma1_start(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, uint
     return true;
 }
 LZ_DEV void lzma1_finish(const Dec &d, const uint8_t *in, const uint8_t *out, lzgpu_result &res) {
+    if (d.hout) push_out(d, (uint64_t)d.pub << 16, (uint64_t)(d.outp - out));
     LZ_IF_LANE0_ONLY {
         res.status = d.status;
         res.err_site = d.site;
@@ -540,6 +573,7 @@ LZ_DEV void lzma2_start(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, uint
     set_shared_addrs<kV>(d, P, io.inbuf, io.stage);
     wc.s_stage = d.sStage;
     d.prog = io.progress;
+    d.hout = io.hout;
     d.out0 = io.out;
     d.pub = 0;
     d.dict_size = u.dict_size;
@@ -744,6 +778,7 @@ LZ_DEV int lzma2_walk(Dec &d, WarpCopy &wc, Lz2Walk &w, uint16_t *P, uint16_t *L
 }
 
 LZ_DEV void lzma2_finish(const Dec &d, const Lz2Walk &w, lzgpu_result &res) {
+    if (d.hout) push_out(d, (uint64_t)d.pub << 16, (uint64_t)(d.outp - w.out));
     LZ_IF_LANE0_ONLY {
         res.status = w.status;
         res.err_site = w.site;

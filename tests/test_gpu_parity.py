@@ -184,12 +184,17 @@ def test_full_size_batch_properties(ctx):
         assert g.status == L.OK and len(g.data) == 1 << 20 and zlib.crc32(g.data) == crcs[i]
 
 
+@pytest.mark.parametrize("push", ["push", "streamed"])
 @pytest.mark.parametrize("shift", [0, 3])
-def test_pinned_host_buffers(ctx, shift, monkeypatch):
+def test_pinned_host_buffers(ctx, shift, push, monkeypatch):
     """Pinned caller buffers take the zero-copy route (units read the compressed input straight from host
-    memory, unit tails written back by one kernel); pageable buffers and LZGPU_NO_ZEROCOPY_IN=1 /
-    LZGPU_NO_TAIL_KERNEL=1 take the slab route.  Same bytes, same results, whatever the alignment."""
+    memory and write their decoded bytes to the caller's buffer themselves, block by block -- or, with
+    LZGPU_NO_PUSH_D2H=1, finished blocks are copied out by the host while the kernel runs and the unit tails by one
+    kernel); pageable buffers and LZGPU_NO_ZEROCOPY_IN=1 / LZGPU_NO_TAIL_KERNEL=1 take the slab route.  Same bytes,
+    same results, whatever the alignment."""
     import torch
+    if push == "streamed":
+        monkeypatch.setenv("LZGPU_NO_PUSH_D2H", "1")
     distinct = 6
     plains = [K.text_block(2000 + i, (1 << 20) - 37 * i) for i in range(distinct)]
     streams = [K.compress_alone(p) for p in plains]
