@@ -163,6 +163,34 @@ LZ_DEV void push_out(const Dec &d, uint64_t from, uint64_t to) {
 #if defined(__CUDA_ARCH__)
     __threadfence_block();   // the bytes were stored by all lanes (and, after an exchange, by other warps of the CTA)
     __syncwarp();
+    // whole 64 KiB blocks between congruent 16-byte-aligned addresses (the usual case: units laid out on 16-byte
+    // boundaries in both buffers): 16-byte loads, eight per lane in flight -- a block is 16 round trips to L2, not 32
+    // trips of five 4-byte loads per vector
+    const uint32_t aligned = __shfl_sync(0xffffffffu, (uint32_t)((((uintptr_t)(d.hout + from) | (uintptr_t)(d.out0 + from) | (uintptr_t)(to - from)) & 15u) == 0), 0);
+    if (aligned) {
+        const uint32_t lane = LZ_LANE();
+        const uint8_t *s = d.out0 + from;
+        uint8_t *t = d.hout + from;
+        const uint64_t nv = (to - from) >> 4;
+        for (uint64_t j0 = 0; j0 < nv; j0 += 256) {                     // uniform trip count
+            uint32_t v[8][4];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint64_t j = j0 + 32u * u + lane;
+                const uint32_t live = j < nv;
+                v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0;
+                asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+                             : "+r"(v[u][0]), "+r"(v[u][1]), "+r"(v[u][2]), "+r"(v[u][3]) : "l"(s + 16u * (live ? j : 0u)), "r"(live) : "memory");
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint64_t j = j0 + 32u * u + lane;
+                const uint32_t live = j < nv;
+                LZ_STG128_IF(t + 16u * (live ? j : 0u), v[u][0], v[u][1], v[u][2], v[u][3], live);
+            }
+        }
+        return;
+    }
     while (from < to) {
         const uint64_t n = to - from < (1u << 20) ? to - from : (uint64_t)(1u << 20);
         warp_copy<true>(d.hout + from, d.out0 + from, (uint32_t)n);
