@@ -42,6 +42,7 @@ struct KArgs {
     uint32_t *progress;          // per unit: decoded bytes that are final in HBM, in 64 KiB blocks (host-mapped; may be null)
     uint8_t *hout_base;          // push mode: device view of the caller's pinned output buffer (else null) ...
     const uint64_t *hout_off;    // ... and where in it each unit's output goes (host-mapped, indexed like `units`)
+    uint32_t *push_stat;         // ... and two counters: time spent pushing whole blocks, blocks pushed (see Dec)
 };
 
 // One warp per CTA, one unit per warp.  Fixed tables (3.7 KB) always in shared
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(32, LZGPU_MIN_CTAS) lzgpu_decode_kernel(const 
     io.inbuf = io.stage + 128;
     io.progress = a.progress ? a.progress + ui : nullptr;
     io.hout = a.hout_base ? a.hout_base + a.hout_off[ui] : nullptr;
+    io.push_stat = a.hout_base ? a.push_stat : nullptr;
     lzgpu_result &res = a.results[ui];
     if (u.kind == LZGPU_KIND_LZMA2_GROUP) run_unit_lzma2<kV>(u, io, P, L, a.lit_bits_cap, res);
     else run_unit_lzma1<kV>(u, io, P, L, res);
@@ -336,6 +338,7 @@ __global__ void __launch_bounds__(32 * kSmMaxSlots, 1) lzgpu_sm_kernel(const KAr
                 io.out_cap = u.out_cap;
                 io.progress = a.progress ? a.progress + ui : nullptr;
                 io.hout = a.hout_base ? a.hout_base + a.hout_off[ui] : nullptr;
+                io.push_stat = a.hout_base ? a.push_stat : nullptr;
                 u_in = io.in;
                 u_out = io.out;
                 resume = false;
@@ -679,6 +682,9 @@ struct DevState {
     // 0.1 - 0.8 s now and then)
     uint8_t *d_litws = nullptr;
     uint64_t litws_cap = 0;
+    // push mode found the link to the host too busy (see run_shard): copy engines until the next probe
+    bool push_slow = false;
+    uint32_t push_skipped = 0;
 };
 
 struct lzgpu_ctx {
@@ -884,7 +890,7 @@ static int plan_create_impl(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *uni
         int nsm = 0;
         if (sched_on && p->variant == 33 && cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->devs[dev_index].device) == cudaSuccess && nsm > 0) {
             bool any = false;
-            for (size_t li = 0; li < p->launches.size() && li < 64; li++) {
+            for (size_t li = 0; li < p->launches.size() && li < 62; li++) {   // (counters 62, 63: push-mode statistics)
                 Launch &L = p->launches[li];
                 if (L.lit_global || L.count == 0) continue;
                 const uint32_t slot_bytes = (uint32_t)((L.smem + 15u) & ~(size_t)15u) + kSmSaveBytes;
@@ -972,6 +978,7 @@ extern "C" int lzgpu_plan_launch(lzgpu_plan *p, const uint8_t *d_in, uint8_t *d_
         CUDA_TRY(cudaEventRecord(ds.fork_ev, st));
         for (int k = 0; k < DevState::kAux; k++) CUDA_TRY(cudaStreamWaitEvent(ds.aux[k], ds.fork_ev, 0));
     }
+    if (p->d_hout_base && p->d_next) CUDA_TRY(cudaMemsetAsync(p->d_next + 62, 0, 2 * sizeof(uint32_t), st));
     int rr = 1;
     for (const Launch &L : p->launches) {
         cudaStream_t ls = st;
@@ -990,6 +997,7 @@ extern "C" int lzgpu_plan_launch(lzgpu_plan *p, const uint8_t *d_in, uint8_t *d_
         a.progress = p->d_progress;
         a.hout_base = p->d_hout_base;
         a.hout_off = p->d_hout_off;
+        a.push_stat = p->d_next ? p->d_next + 62 : nullptr;   // the last two of the plan's 64 counters
         size_t smem = L.smem;
         if (p->max_ctas_per_sm >= 5) {
             // occupancy cap (experiments, and the single-wave heuristic of plan_create): asking for more shared memory
@@ -1348,7 +1356,16 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
     // Push mode: when the caller's output buffer is pinned and mapped, every unit writes its decoded bytes there itself,
     // over PCIe, 64 KiB block by block as they become final and its tail when it ends (push_out, lzgpu_unit.cuh): no
     // D2H copy, no polling thread, nothing left to do when the kernel ends.  (LZGPU_NO_PUSH_D2H=1: the streamed copies.)
+    // Push mode holds the decoding warps up when the host cannot take the bytes as fast as they come (measured: eight
+    // GPUs of one node, 78 GB/s of output against the ~69 GB/s the host ingests: 135 ms per step where the copy engines
+    // need 125).  The units time their block pushes; a shard that needed more than kPushSlowKc kilo-cycles per 64 KiB
+    // block (one GPU: ~130) makes this device use the streamed copies, and push mode is probed again every 64th call.
+    constexpr uint32_t kPushSlowKc = 600;
     bool push = zc_out != nullptr && !getenv("LZGPU_NO_PUSH_D2H");
+    if (push && ds.push_slow && !getenv("LZGPU_PUSH_D2H")) {
+        if (++ds.push_skipped < 64) push = false;
+        else ds.push_skipped = 0;
+    }
     bool stream_out = !push && sh.out_bytes >= ((uint64_t)32 << 20) && !getenv("LZGPU_NO_STREAM_D2H");
     if (stream_out || push) {
         if (stream_out && !ds.copy_stream && cudaStreamCreateWithFlags(&ds.copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); stream_out = false; }
@@ -1433,6 +1450,15 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
     if (sh.rc == 0) {
         rc = lzgpu_plan_results(plan, tmp.data(), &st);   // waits for the kernel
         if (rc != LZGPU_E_OK) { sh.rc = rc; sh.err = g_last_error; }
+    }
+    if (sh.rc == 0 && push && plan->d_next) {
+        uint32_t ps[2] = {0, 0};
+        if (cudaMemcpy(ps, plan->d_next + 62, sizeof ps, cudaMemcpyDeviceToHost) == cudaSuccess && ps[1] >= 32u * 64u) {
+            const uint32_t kc_per_block = ps[0] / ps[1];
+            ds.push_slow = kc_per_block > kPushSlowKc;
+            if (trace) fprintf(stderr, "[lzgpu dev %d] push mode: %u kilo-cycles per 64 KiB block over %u blocks%s\n", ds.device,
+                               kc_per_block, ps[1] / 32u, ds.push_slow ? " -> streamed copies from the next call on" : "");
+        } else cudaGetLastError();
     }
     if (sh.rc == 0 && stream_out) {
         if (zc_out) {

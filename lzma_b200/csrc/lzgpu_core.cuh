@@ -143,6 +143,7 @@ struct Dec {
     const uint8_t *out0;            // start of the unit's output
     uint32_t pub;                   // blocks published (or pushed) so far
     uint8_t *hout;                  // push mode: where this unit's output goes in the caller's pinned buffer (device view), or null
+    uint32_t *push_stat;            // push mode: [0] += kilo-cycles spent pushing whole blocks, [1] += blocks (both x 32: every lane adds)
 };
 
 // Input is consumed through a 64-bit lookahead register so that the per-bit

@@ -168,6 +168,9 @@ LZ_DEV void push_out(const Dec &d, uint64_t from, uint64_t to) {
     // trips of five 4-byte loads per vector
     const uint32_t aligned = __shfl_sync(0xffffffffu, (uint32_t)((((uintptr_t)(d.hout + from) | (uintptr_t)(d.out0 + from) | (uintptr_t)(to - from)) & 15u) == 0), 0);
     if (aligned) {
+        // timed: the host switches to copy-engine transfers when the link is so busy (eight GPUs of a node writing
+        // to host memory at once) that these stores hold the decoder up
+        const long long t0 = clock64();
         const uint32_t lane = LZ_LANE();
         const uint8_t *s = d.out0 + from;
         uint8_t *t = d.hout + from;
@@ -188,6 +191,10 @@ LZ_DEV void push_out(const Dec &d, uint64_t from, uint64_t to) {
                 const uint32_t live = j < nv;
                 LZ_STG128_IF(t + 16u * (live ? j : 0u), v[u][0], v[u][1], v[u][2], v[u][3], live);
             }
+        }
+        if (d.push_stat) {
+            const uint32_t kc = (uint32_t)((unsigned long long)(clock64() - t0) >> 10), nb = (uint32_t)((to - from) >> 16);
+            asm volatile("red.global.add.u32 [%0], %1;\n\tred.global.add.u32 [%0+4], %2;" : : "l"(d.push_stat), "r"(kc), "r"(nb) : "memory");
         }
         return;
     }
@@ -515,6 +522,7 @@ struct UnitIO {
     uint8_t *inbuf;          // kF2Stage bytes of shared memory, 16-byte aligned (V_CHAIN input stage)
     uint32_t *progress;      // host-mapped progress counter of this unit (streamed D2H), or null
     uint8_t *hout;           // push mode: the unit's output range in the caller's pinned buffer (device view), or null
+    uint32_t *push_stat;     // push mode: two counters of the launch (Dec::push_stat), or null
 };
 
 // LZMA1 unit (kind RAW; ALONE units are converted by the host): set-up, symbol loop, verdict.  The three are separate so
@@ -533,6 +541,7 @@ LZ_DEV bool lzma1_start(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, uint
     wc.s_stage = d.sStage;
     d.prog = io.progress;
     d.hout = io.hout;
+    d.push_stat = io.push_stat;
     d.out0 = io.out;
     d.pub = 0;
     d.dict_size = u.dict_size;
@@ -602,6 +611,7 @@ LZ_DEV void lzma2_start(const lzgpu_unit &u, const UnitIO &io, uint16_t *P, uint
     wc.s_stage = d.sStage;
     d.prog = io.progress;
     d.hout = io.hout;
+    d.push_stat = io.push_stat;
     d.out0 = io.out;
     d.pub = 0;
     d.dict_size = u.dict_size;

@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(32, 14) k1(const KArgs a) {
     const lzgpu_unit u = a.units[ui];
     uint16_t *P = smem_probs, *L = smem_probs + LZ_LAY(kV)::LIT;
     UnitIO io; io.in = a.in_base + u.in_off; io.in_len = u.in_len; io.out = a.out_base + u.out_off; io.out_cap = u.out_cap;
-    io.stage = reinterpret_cast<uint8_t *>(smem_probs + a.stage_off); io.inbuf = io.stage + 128; io.progress = a.progress ? a.progress + ui : nullptr; io.hout = nullptr;
+    io.stage = reinterpret_cast<uint8_t *>(smem_probs + a.stage_off); io.inbuf = io.stage + 128; io.progress = a.progress ? a.progress + ui : nullptr; io.hout = nullptr; io.push_stat = nullptr;
     run_unit_lzma1<kV>(u, io, P, L, a.results[ui]);
 }
 template __global__ void k1<97>(const KArgs);

@@ -53,6 +53,7 @@ extern "C" int emu_decode_batch(const lzgpu_unit *units, int64_t n, const uint8_
         io.inbuf = inbuf;
         io.progress = nullptr;
         io.hout = nullptr;
+        io.push_stat = nullptr;
 #define EMU_RUN(V) do { if (pb2) run_one<(V) | V_PB2>(u, io, P, L, bits, r); else run_one<(V)>(u, io, P, L, bits, r); } while (0)
         switch (variant) {
             case 0: EMU_RUN(0); break;
