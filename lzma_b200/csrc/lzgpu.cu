@@ -1360,7 +1360,8 @@ void run_shard(lzgpu_ctx *ctx, int dev_index, Shard &sh, const uint8_t *in_base,
     // GPUs of one node, 78 GB/s of output against the ~69 GB/s the host ingests: 135 ms per step where the copy engines
     // need 125).  The units time their block pushes; a shard that needed more than kPushSlowKc kilo-cycles per 64 KiB
     // block (one GPU: ~130) makes this device use the streamed copies, and push mode is probed again every 64th call.
-    constexpr uint32_t kPushSlowKc = 600;
+    uint32_t kPushSlowKc = 600;
+    if (const char *e = getenv("LZGPU_PUSH_SLOW_KC")) kPushSlowKc = (uint32_t)atoi(e);   // (tests: 0 = every shard counts as slow)
     bool push = zc_out != nullptr && !getenv("LZGPU_NO_PUSH_D2H");
     if (push && ds.push_slow && !getenv("LZGPU_PUSH_D2H")) {
         if (++ds.push_skipped < 64) push = false;

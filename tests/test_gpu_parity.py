@@ -224,6 +224,33 @@ def test_pinned_host_buffers(ctx, shift, push, monkeypatch):
     assert res[n + 1].status == L.OK_INPUT_EXHAUSTED
 
 
+def test_push_mode_falls_back_to_streamed_copies(monkeypatch):
+    """Push mode times its block pushes; a shard that found the link to the host too busy (here: any shard, threshold 0)
+    makes its device take the copy-engine path from the next call on.  Both paths must leave the same bytes."""
+    import torch
+    monkeypatch.setenv("LZGPU_PUSH_SLOW_KC", "0")
+    plains = [K.text_block(2300 + i, 1 << 20) for i in range(4)]
+    streams = [K.compress_alone(p) for p in plains]
+    n = 80                                             # 80 MiB: enough blocks to judge, enough bytes for the streamed path
+    ss = [streams[i % 4] for i in range(n)]
+    units, in_np, out_size, _ = B.build_alone_batch(ss, [1 << 20] * n)
+    pin_in = torch.from_numpy(in_np.copy()).pin_memory()
+    pin_out = torch.empty(out_size, dtype=torch.uint8).pin_memory()
+    with B.Context([0]) as c:
+        outs, d2h = [], []
+        for _ in range(3):
+            pin_out.fill_(0xEE)
+            res, st = c.decode_batch(units, pin_in.numpy(), pin_out.numpy())
+            assert all(r.status == L.OK and r.bytes_out == 1 << 20 for r in res)
+            outs.append(pin_out.numpy().copy())
+            d2h.append(st.d2h_ms)
+    for k, u in enumerate(units):
+        want = plains[k % 4]
+        for o in outs:
+            assert o[u.out_off:u.out_off + (1 << 20)].tobytes() == want, k
+    assert d2h[0] < d2h[1] and d2h[0] < d2h[2], d2h      # first call pushed (nothing after the kernel), later ones streamed (unit tails follow it)
+
+
 def test_library_pinned_buffers(ctx):
     """lzgpu_alloc_pinned: what a cgo caller uses for its buffers; the batch call takes the zero-copy route on them."""
     lib = L.lib()
