@@ -170,9 +170,17 @@ int lzgpu_ctx_create(const int *devices, int n_devices, lzgpu_ctx **ctx);
 void lzgpu_ctx_destroy(lzgpu_ctx *ctx);
 int lzgpu_ctx_device_count(const lzgpu_ctx *ctx);
 
-/* The batch entry point with HOST buffers (pinned recommended).  Shards the
- * units over the context's devices by compressed size, copies each shard's
- * input up, decodes, copies the output and results back.  Synchronous.
+/* The batch entry point with HOST buffers.  Shards the units over the context's
+ * devices by compressed size, decodes, returns output and results.  Synchronous.
+ * With PINNED, mapped buffers (lzgpu_alloc_pinned, cudaHostAlloc / cudaHostRegister,
+ * torch's pinned tensors) nothing is copied ahead of or after the kernel: the units
+ * read their compressed input from the caller's buffer over PCIe while they decode,
+ * and write every finished 64 KiB block of output and their tail into the caller's
+ * buffer themselves ("push mode"; only the bytes a unit decoded, only to its range).
+ * When the host cannot take the bytes as fast as they come (all GPUs of a node
+ * writing at once) a device falls back to copy-engine transfers overlapped with the
+ * kernel by itself; pageable buffers always go through device slabs and copies.
+ * Environment: LZGPU_NO_ZEROCOPY_IN, LZGPU_NO_PUSH_D2H, LZGPU_PUSH_D2H, LZGPU_TRACE.
  * Returns LZGPU_E_OK when the batch executed (per-unit outcome in results[]).
  * Replaces, for many streams at once, NewReader1/NewReader2 + io.Copy
  * (reader1.go:18,223; reader2.go:26,216). */
