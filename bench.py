@@ -766,7 +766,7 @@ def main():
                            "d2h_bytes_per_step": int(g_out), "ms_per_step": e2e_t_max * 1e3, "steps": args.steps,
                            "gpu_launches_per_step": e2e["launches"],
                            "rank0_breakdown_ms": {"h2d": e2e["h2d_ms"], "kernel": e2e["kernel_ms"], "d2h": e2e["d2h_ms"]},
-                           "api": "lzgpu_decode_batch (pinned host buffers; the units read the compressed input from host memory over PCIe while they decode, finished 64 KiB output blocks are copied out while the kernel runs)"}
+                           "api": "lzgpu_decode_batch (pinned host buffers; the units read the compressed input from host memory over PCIe while they decode and write every finished 64 KiB block of output into the caller's buffer themselves; a device falls back to copy-engine transfers overlapped with the kernel when the host cannot keep up)"}
         line.update(sub)
         if not args.no_cpu_baseline:
             idx = cpu_sample(distinct, cores, args.streams)
