@@ -963,6 +963,7 @@ extern "C" int lzgpu_plan_launch(lzgpu_plan *p, const uint8_t *d_in, uint8_t *d_
     CUDA_TRY(cudaSetDevice(ds.device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ds.stream;
     CUDA_TRY(cudaEventRecord(p->ev0, st));
+    if (p->d_hout_base && p->d_next) CUDA_TRY(cudaMemsetAsync(p->d_next + 62, 0, 2 * sizeof(uint32_t), st));   // push-mode statistics (before the fork below)
     // A mixed batch has one launch per table class (literal-table size x posState-table size), and a launch lasts as
     // long as its longest unit: classes are independent, so they run side by side on auxiliary streams, forked from
     // and joined back into the caller's stream.  (Launches that share the HBM literal workspace stay on one stream.)
@@ -978,7 +979,6 @@ extern "C" int lzgpu_plan_launch(lzgpu_plan *p, const uint8_t *d_in, uint8_t *d_
         CUDA_TRY(cudaEventRecord(ds.fork_ev, st));
         for (int k = 0; k < DevState::kAux; k++) CUDA_TRY(cudaStreamWaitEvent(ds.aux[k], ds.fork_ev, 0));
     }
-    if (p->d_hout_base && p->d_next) CUDA_TRY(cudaMemsetAsync(p->d_next + 62, 0, 2 * sizeof(uint32_t), st));
     int rr = 1;
     for (const Launch &L : p->launches) {
         cudaStream_t ls = st;
