@@ -892,7 +892,7 @@ static int plan_create_impl(lzgpu_ctx *ctx, int dev_index, const lzgpu_unit *uni
             bool any = false;
             for (size_t li = 0; li < p->launches.size() && li < 62; li++) {   // (counters 62, 63: push-mode statistics)
                 Launch &L = p->launches[li];
-                if (L.lit_global || L.count == 0) continue;
+                if (L.lit_global || L.count == 0 || L.count > (1u << 26)) continue;   // (the unit counter advances by 32 per fetch)
                 const uint32_t slot_bytes = (uint32_t)((L.smem + 15u) & ~(size_t)15u) + kSmSaveBytes;
                 uint32_t smax = std::min<uint32_t>(kSmMaxSlots, (232448u - kSmCtlBytes) / slot_bytes);
                 if (p->max_ctas_per_sm > 0) smax = std::min<uint32_t>(smax, (uint32_t)p->max_ctas_per_sm);
