@@ -82,7 +82,7 @@ func NewEngine() (*Engine, error) {
 func (e *Engine) Close() { C.lzgpu_ctx_destroy(e.ctx); e.ctx = nil }
 
 // PinnedBuffer is host memory the GPUs can address (lzgpu_alloc_pinned): input placed in one is read by the
-// decode kernel directly over PCIe, output written to one is streamed back while the kernel runs.
+// decode kernel directly over PCIe, output written to one is written there by the decoding units themselves, block by block, while the kernel runs.
 type PinnedBuffer struct {
 	p unsafe.Pointer
 	B []byte
@@ -158,7 +158,7 @@ func (e *Engine) DecodeBatch(units []Unit) ([]Result, error) {
 }
 
 // DecodeBatchPinned is DecodeBatch with caller-held page-locked buffers: the compressed inputs are laid into
-// in.B (read by the kernel straight from host memory) and the decoded bytes land in out.B (streamed back while
+// in.B (read by the kernel straight from host memory) and the decoded bytes land in out.B (written by the units themselves while
 // the kernel runs). The Results' Out slices alias out.B and are valid until the caller reuses or frees it.
 // ErrOutputOverflow-style sizing is the caller's: len(in.B) / len(out.B) must cover the laid-out units.
 func (e *Engine) DecodeBatchPinned(units []Unit, in, out *PinnedBuffer) ([]Result, error) {
