@@ -127,14 +127,28 @@ def _compile(text):
     return prog, labels, regs
 
 
+class OutOfBounds(Exception):
+    pass
+
+
 class Shared:
-    def __init__(self, size):
+    """Flat shared memory with bounds: [0, table_end) holds uint16 probability cells (the only place a block may store
+    to, and where its 16-bit loads must lie), [in_lo, in_hi) the staged input (8-bit loads only)."""
+
+    def __init__(self, size, table_end=None, in_lo=None, in_hi=None):
         self.b = bytearray(size)
+        self.table_end, self.in_lo, self.in_hi = table_end, in_lo, in_hi
 
     def ld(self, a, n):
+        if self.table_end is not None:
+            ok = (a + n <= self.table_end and a % 2 == 0) if n == 2 else (self.in_lo <= a < self.in_hi)
+            if not ok:
+                raise OutOfBounds(f"{n}-byte load at {a:#x}")
         return int.from_bytes(self.b[a:a + n], "little")
 
     def st(self, a, n, v):
+        if self.table_end is not None and not (n == 2 and a % 2 == 0 and a + 2 <= self.table_end):
+            raise OutOfBounds(f"{n}-byte store at {a:#x}")
         self.b[a:a + n] = (v & ((1 << (8 * n)) - 1)).to_bytes(n, "little")
 
 

@@ -70,7 +70,8 @@ class Fast:
         self.sP = 0
         self.sL = 2 * self.Y.LIT
         self.sIn = (2 * ncells + 15) & ~15
-        self.sm = I.Shared(self.sIn + len(payload) + 64)
+        # bounds: stores and 16-bit loads inside the tables only; input bytes from the staged input (+ the byte ahead) only
+        self.sm = I.Shared(self.sIn + len(payload) + 64, table_end=2 * ncells, in_lo=self.sIn, in_hi=self.sIn + len(payload) - 5 + 1)
         for c in range(ncells):
             self.sm.st(2 * c, 2, 1024)
         self.sm.b[self.sIn:self.sIn + len(payload) - 5] = payload[5:]
@@ -104,6 +105,9 @@ class Fast:
 
     def lds16(self, a):
         return self.sm.ld(a, 2)
+
+    class Rejected(Exception):
+        """the C++ around the blocks would leave the fast decoder here (bad distance, rep on an empty window)"""
 
     def next_ctx(self):
         Y = self.Y
@@ -210,9 +214,10 @@ class Fast:
                     if self.rep[0] == 0xFFFFFFFF:
                         self.eos = True
                         return
-                    raise AssertionError("distance beyond the window: %#x" % self.rep[0])
+                    raise Fast.Rejected("distance beyond the window: %#x" % self.rep[0])
             else:                                                  # rep match
-                assert self.wpos or self.full
+                if not (self.wpos or self.full):
+                    raise Fast.Rejected("rep match on an empty window")
                 short_rep = False
                 a = a_rep_cur + 2
                 bit = self.bit(self.lds16(a), a)
@@ -238,7 +243,8 @@ class Fast:
                 self.bump(ln)
                 self.next_ctx()
             d = self.rep[0] + 1
-            assert d <= len(self.out)
+            if d > len(self.out):
+                raise Fast.Rejected("rep distance beyond the window")
             for _ in range(ln):
                 self.out.append(self.out[-d])
 
@@ -275,9 +281,40 @@ def test_long_distances_and_repeats(blocks):
     r = random.Random(9)
     base = bytes(r.randrange(256) for _ in range(3000))
     plain = bytearray()
-    while len(plain) < 300_000:
+    while len(plain) < 160_000:
         plain += base[: r.randrange(20, 400)]
         plain += bytes(r.randrange(256) for _ in range(r.randrange(0, 6)))
         if r.random() < 0.05:
             plain += bytes(r.randrange(256) for _ in range(2500))
-    _check(blocks, bytes(plain[:300_000]), 300_000, dict_size=1 << 20)
+    _check(blocks, bytes(plain[:160_000]), 160_000, dict_size=1 << 20)
+
+
+def test_hostile_streams_stay_inside_the_tables(blocks):
+    """compute-sanitizer is closed on this pool; the interpreter's shared memory has bounds instead.  Damaged streams
+    -- flipped, overwritten, inserted bytes inside the range-coded part -- drive the ladders with garbage: every store
+    and every 16-bit load must stay inside the probability tables, every input byte inside the staged input, whatever
+    is decoded (the C++ around the blocks rejects bad distances; wrong bytes are what a damaged stream gives)."""
+    import random
+    r = random.Random(4)
+    plains = [K.text_block(91, 24 << 10), K.mixed_block(92, 24 << 10), K.random_block(93, 4 << 10)]
+    n_run = 0
+    for plain in plains:
+        for lc, lp, pb in ((3, 0, 2), (0, 4, 4), (4, 0, 0)):
+            good = K.compress_alone(plain, lc=lc, lp=lp, pb=pb)
+            for _ in range(3):
+                s = bytearray(good)
+                for _ in range(r.randrange(1, 4)):
+                    kind, pos = r.randrange(3), r.randrange(18, len(s) - 8)
+                    if kind == 0:
+                        s[pos] ^= 1 << r.randrange(8)
+                    elif kind == 1:
+                        s[pos:pos + r.randrange(1, 6)] = bytes(r.randrange(256) for _ in range(r.randrange(1, 6)))
+                    else:
+                        s[pos:pos] = bytes(r.randrange(256) for _ in range(r.randrange(1, 4)))
+                f = Fast(blocks, bytes(s), len(plain))
+                try:
+                    f.run()
+                except Fast.Rejected:
+                    pass
+                n_run += 1
+    assert n_run == 27
